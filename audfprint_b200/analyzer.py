@@ -1,0 +1,388 @@
+"""Analyzer — drop-in mirror of audfprint_analyze.Analyzer whose arithmetic
+runs in libafp.so (sm_100a CUDA) through the C ABI of include/afp.h.
+
+Same attribute names, method names, argument meaning and error behaviour as the
+reference class (audfprint_analyze.py:115-457); the module-level helpers
+landmarks2hashes / hashes2landmarks and the .afpt/.afpk codecs (:81-112,
+:460-514) are provided too.  Host code here is bookkeeping only: parameter
+tables, buffer packing, result unpacking.  Nothing in this file computes a
+spectrogram, a peak or a hash on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import wave
+
+import numpy as np
+
+from . import _lib
+
+# Special extensions of precomputed files (audfprint_analyze.py:29-32)
+PRECOMPEXT = '.afpt'
+PRECOMPPKEXT = '.afpk'
+
+DENSITY = 20.0
+OVERSAMP = 1
+N_FFT = 512
+N_HOP = 256
+HPF_POLE = 0.98
+
+# hash packing (audfprint_analyze.py:69-78)
+F1_BITS, DF_BITS, DT_BITS = 8, 6, 6
+B1_MASK = (1 << F1_BITS) - 1
+B1_SHIFT = DF_BITS + DT_BITS
+DF_MASK = (1 << DF_BITS) - 1
+DF_SHIFT = DT_BITS
+DT_MASK = (1 << DT_BITS) - 1
+
+
+def landmarks2hashes(landmarks):
+    """(time, bin1, bin2, dtime) rows -> int32 (L,2) [time, hash]
+    (audfprint_analyze.py:81-96).  Pure bit packing of values the device
+    produced; kept on the host for API parity (<1 % of the reference's time)."""
+    landmarks = np.array(landmarks)
+    if landmarks.shape[0] == 0:
+        return np.zeros((0, 2), dtype=np.int32)
+    hashes = np.zeros((landmarks.shape[0], 2), dtype=np.int32)
+    hashes[:, 0] = landmarks[:, 0]
+    hashes[:, 1] = (((landmarks[:, 1] & B1_MASK) << B1_SHIFT)
+                    | (((landmarks[:, 2] - landmarks[:, 1]) & DF_MASK) << DF_SHIFT)
+                    | (landmarks[:, 3] & DT_MASK))
+    return hashes
+
+
+def hashes2landmarks(hashes):
+    """Inverse of landmarks2hashes (audfprint_analyze.py:99-112)."""
+    out = []
+    for time_, hash_ in hashes:
+        dtime = hash_ & DT_MASK
+        bin1 = (hash_ >> B1_SHIFT) & B1_MASK
+        dbin = (hash_ >> DF_SHIFT) & DF_MASK
+        if dbin >= (1 << (DF_BITS - 1)):
+            dbin -= (1 << DF_BITS)
+        out.append((time_, bin1, bin1 + dbin, dtime))
+    return out
+
+
+def _wav_reader(filename, sr=None, channels=None):
+    """Minimal PCM-WAV reader standing in for audio_read.audio_read
+    (audio_read.py:56-68; ffmpeg decode/resample is out of scope).
+    Returns (float32 samples in [-1,1), sr) like the reference reader does
+    (audio_read.py:139-145).  Down-mixes to mono; refuses to resample."""
+    with wave.open(filename, 'rb') as w:
+        nch, width, fs, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        if width != 2:
+            raise IOError("only 16-bit PCM WAV is supported, got %d-byte samples" % width)
+        raw = np.frombuffer(w.readframes(n), dtype='<i2')
+    if nch > 1:
+        raw = raw.reshape(-1, nch)
+        data = np.mean(raw.astype(np.float32) * np.float32(1.0 / 32768.0), axis=-1).astype(np.float32)
+    else:
+        data = raw.astype(np.float32) * np.float32(1.0 / 32768.0)
+    if sr is not None and fs != sr:
+        raise IOError("%s is sampled at %d Hz, need %d Hz (no resampler in this build)" % (filename, fs, sr))
+    return data, fs
+
+
+def _as_pcm(d):
+    """Normalise one signal to a contiguous int16 or float32 1-D array."""
+    a = np.asarray(d)
+    if a.ndim != 1:
+        raise ValueError("signal must be 1-D")
+    if a.dtype == np.int16:
+        return np.ascontiguousarray(a), _lib.PCM_I16
+    if a.dtype != np.float32:
+        # the reference reader yields float32 (audio_read.py:145); wider input is narrowed
+        a = a.astype(np.float32)
+    return np.ascontiguousarray(a), _lib.PCM_F32
+
+
+class Analyzer(object):
+    """Parameters + methods of the reference Analyzer (audfprint_analyze.py:115-151)."""
+
+    def __init__(self, density=DENSITY, device=None):
+        self.density = density
+        self.target_sr = 11025
+        self.n_fft = N_FFT
+        self.n_hop = N_HOP
+        self.shifts = 1
+        self.f_sd = 30.0
+        self.maxpksperframe = 5
+        self.maxpairsperpeak = 3
+        self.targetdf = 31
+        self.mindt = 2
+        self.targetdt = 63
+        self.soundfiledur = 0.0
+        self.soundfiletotaldur = 0.0
+        self.soundfilecount = 0
+        self.fail_on_error = True
+        # not in the reference: which GPU, and the pluggable file reader
+        self.device = device
+        self.reader = _wav_reader
+
+    # objects are pickled into worker processes by the reference CLI
+    # (audfprint.py:218-223,249-265): carry only plain attributes
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if st.get("reader") is _wav_reader:
+            st["reader"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        if self.reader is None:
+            self.reader = _wav_reader
+
+    # ---- device configuration -------------------------------------------------
+    def _a_dec(self):
+        # audfprint_analyze.py:277, same expression -> same double
+        return float((1 - 0.01 * (self.density * np.sqrt(self.n_hop / 352.8) / 35)) ** (1 / OVERSAMP))
+
+    def _configure(self, shifts):
+        if self.n_fft != N_FFT or self.n_hop != N_HOP:
+            raise ValueError("libafp is compiled for n_fft=512, n_hop=256")
+        ctx = _lib.context(self.device)
+        key = (float(self.density), float(self.f_sd), int(self.maxpksperframe), int(self.maxpairsperpeak),
+               int(self.targetdf), int(self.mindt), int(self.targetdt), int(shifts))
+        if ctx.analyzer_key != key:
+            p = _lib.AnalyzerParams(self._a_dec(), HPF_POLE ** (1 / OVERSAMP), int(self.maxpksperframe),
+                                    int(self.maxpairsperpeak), int(self.targetdf), int(self.mindt),
+                                    int(self.targetdt), int(shifts))
+            # the very doubles the reference multiplies by (audfprint_analyze.py:279, :187-192)
+            win = np.ascontiguousarray(np.hanning(self.n_fft + 2)[1:-1], dtype=np.float64)
+            npts = self.n_fft // 2
+            gauss = np.ascontiguousarray(
+                np.exp(-0.5 * ((np.arange(-npts, npts + 1) / self.f_sd) ** 2)), dtype=np.float64)
+            ctx.check(ctx.lib.afp_set_analyzer(ctx.h, C.byref(p), win.ctypes.data, gauss.ctypes.data,
+                                               float(self.f_sd)))
+            ctx.analyzer_key = key
+        return ctx
+
+    # ---- batch entry points (the throughput path) -------------------------------
+    def fingerprint_packed(self, pcm, sample_offsets, shifts=None, fetch=True, host_rows=None,
+                           sample_lengths=None):
+        """Fingerprint nfiles signals packed in one buffer.
+
+        pcm             int16/float32 numpy array (host) or torch tensor (CUDA or pinned host)
+        sample_offsets  int64 [nfiles+1] start of each file in `pcm`
+        sample_lengths  int64 [nfiles] or None (= offsets[i+1]-offsets[i]); lets files be
+                        padded to 16-byte boundaries (TMA staging)
+        returns (rows int32 (U,2), row_offsets int64 (nfiles+1)) — rows of file i
+        are rows[row_offsets[i]:row_offsets[i+1]], sorted by (time, hash).
+        With fetch=False nothing is copied back (results stay in the workspace)."""
+        shifts = self.shifts if shifts is None else shifts
+        shifts = max(1, int(shifts))
+        ctx = self._configure(shifts)
+        off = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        nfiles = len(off) - 1
+        lens = None if sample_lengths is None else np.ascontiguousarray(sample_lengths, dtype=np.int64)
+        lens_p = None if lens is None else lens.ctypes.data_as(C.POINTER(C.c_int64))
+        ptr, on_host = _lib.ptr_of(pcm)
+        if isinstance(pcm, np.ndarray):
+            dtype = {np.dtype(np.int16): _lib.PCM_I16, np.dtype(np.float32): _lib.PCM_F32}[pcm.dtype]
+        else:
+            dtype = _lib.PCM_I16 if pcm.element_size() == 2 else _lib.PCM_F32
+        total = C.c_int64(-1)
+        ctx.check(ctx.lib.afp_fingerprint_batch(ctx.h, ptr, dtype, on_host, nfiles,
+                                                off.ctypes.data_as(C.POINTER(C.c_int64)), lens_p,
+                                                C.byref(total) if fetch else None))
+        if not fetch:
+            return None, None
+        rows = host_rows if host_rows is not None else np.empty((max(int(total.value), 0), 2), np.int32)
+        roff = np.empty(nfiles + 1, np.int64)
+        rptr, r_on_host = _lib.ptr_of(rows)
+        ctx.check(ctx.lib.afp_fetch_hashes(ctx.h, rptr, r_on_host, roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        if host_rows is not None:
+            rows = rows[:int(total.value)]
+        return rows, roff
+
+    def fingerprint_batch(self, signals, shifts=None):
+        """List of 1-D signals (int16 or float) -> list of int32 (U,2) hash arrays."""
+        if len(signals) == 0:
+            return []
+        arrs = [_as_pcm(s) for s in signals]
+        kinds = set(k for _, k in arrs)
+        if len(kinds) > 1:
+            arrs = [(a.astype(np.float32) * np.float32(1.0 / 32768.0) if k == _lib.PCM_I16 else a, _lib.PCM_F32)
+                    for a, k in arrs]
+        lens = np.array([len(a) for a, _ in arrs], np.int64)
+        # keep every file 16-byte aligned in the packed buffer (TMA bulk copies)
+        esz = arrs[0][0].dtype.itemsize
+        al = 16 // esz
+        starts = np.zeros(len(arrs) + 1, np.int64)
+        for i, n in enumerate(lens):
+            starts[i + 1] = starts[i] + (n + al - 1) // al * al
+        packed = np.zeros(int(starts[-1]) + al, arrs[0][0].dtype)
+        for (a, _), s in zip(arrs, starts[:-1]):
+            packed[s:s + len(a)] = a
+        rows, roff = self.fingerprint_packed(packed, starts, shifts, sample_lengths=lens)
+        return [rows[roff[i]:roff[i + 1]] for i in range(len(arrs))]
+
+    # ---- reference methods -------------------------------------------------------
+    def find_peaks(self, d, sr):
+        """Waveform -> list of (time_frame, freq_bin) (audfprint_analyze.py:255-308)."""
+        if len(d) == 0:
+            return []
+        a, dtype = _as_pcm(d)
+        ctx = self._configure(1)
+        off = np.array([0, len(a)], np.int64)
+        ctx.check(ctx.lib.afp_fingerprint_batch(ctx.h, a.ctypes.data, dtype, 1, 1,
+                                                off.ctypes.data_as(C.POINTER(C.c_int64)), None, None))
+        return self._fetch_peaks(ctx, 0, 1)[0]
+
+    def _fetch_peaks(self, ctx, shift, nfiles):
+        poff = np.empty(nfiles + 1, np.int64)
+        ctx.check(ctx.lib.afp_fetch_peaks(ctx.h, shift, None, 1, poff.ctypes.data_as(C.POINTER(C.c_int64))))
+        rows = np.empty((int(poff[-1]), 2), np.int32)
+        ctx.check(ctx.lib.afp_fetch_peaks(ctx.h, shift, rows.ctypes.data, 1, None))
+        return [[(int(c), int(b)) for c, b in rows[poff[i]:poff[i + 1]]] for i in range(nfiles)]
+
+    def peaks2landmarks(self, pklist):
+        """(col, bin) list -> (col, bin1, bin2, dt) list (audfprint_analyze.py:310-343)."""
+        if len(pklist) == 0:
+            return []
+        rows = np.ascontiguousarray(np.array(pklist, dtype=np.int32).reshape(-1, 2))
+        ctx = self._configure(1)
+        n = C.c_int64(0)
+        ctx.check(ctx.lib.afp_landmarks_from_peaks(ctx.h, rows.ctypes.data, len(rows), 1, C.byref(n)))
+        out = np.empty((int(n.value), 4), np.int32)
+        ctx.check(ctx.lib.afp_fetch_landmarks(ctx.h, out.ctypes.data, 1))
+        return [tuple(int(v) for v in r) for r in out]
+
+    def spreadpeaksinvector(self, vector, width=4.0):
+        raise NotImplementedError("spreadpeaksinvector is fused into the peak kernel (afp_peaks.cu); "
+                                  "it is not exposed as a separate call")
+
+    def _read(self, filename):
+        try:
+            d, sr = self.reader(filename, sr=self.target_sr, channels=1)
+        except Exception as e:
+            message = "wavfile2peaks: Error reading " + filename
+            if self.fail_on_error:
+                print(e)
+                raise IOError(message)
+            print(message, "skipping")
+            d, sr = [], self.target_sr
+        return d, sr
+
+    def _account(self, dur):
+        self.soundfiledur = dur
+        self.soundfiletotaldur += dur
+        self.soundfilecount += 1
+
+    def wavfile2peaks(self, filename, shifts=None):
+        """Soundfile -> peaks, or list of peak lists when shifts > 1
+        (audfprint_analyze.py:345-383)."""
+        ext = os.path.splitext(filename)[1]
+        if ext == PRECOMPPKEXT:
+            peaks = peaks_load(filename)
+            dur = np.max(peaks, axis=0)[0] * self.n_hop / self.target_sr
+        else:
+            d, sr = self._read(filename)
+            dur = len(d) / sr
+            if shifts is None or shifts < 2:
+                peaks = self.find_peaks(d, sr)
+            elif len(d) == 0:
+                peaks = [[] for _ in range(shifts)]
+            else:
+                # NB the reference takes the offsets from self.shifts (:375)
+                a, dtype = _as_pcm(d)
+                ctx = self._configure(self.shifts)
+                off = np.array([0, len(a)], np.int64)
+                ctx.check(ctx.lib.afp_fingerprint_batch(ctx.h, a.ctypes.data, dtype, 1, 1,
+                                                        off.ctypes.data_as(C.POINTER(C.c_int64)), None, None))
+                peaks = [self._fetch_peaks(ctx, s, 1)[0] for s in range(min(shifts, self.shifts))]
+        self._account(dur)
+        return peaks
+
+    def wavfile2hashes(self, filename):
+        """Soundfile -> int32 (U,2) [time, hash] rows (audfprint_analyze.py:385-426)."""
+        ext = os.path.splitext(filename)[1]
+        if ext == PRECOMPEXT:
+            hashes = hashes_load(filename)
+            dur = np.max(hashes, axis=0)[0] * self.n_hop / self.target_sr
+            self._account(dur)
+            return hashes
+        if ext == PRECOMPPKEXT:
+            peaks = self.wavfile2peaks(filename, self.shifts)
+            if len(peaks) == 0:
+                return []
+            rows = landmarks2hashes(self.peaks2landmarks(peaks))
+            key = np.unique((rows[:, 0].astype(np.uint64) << np.uint64(32)) + rows[:, 1].astype(np.uint64))
+            return np.stack([key >> np.uint64(32), key & np.uint64(0xFFFFFFFF)], axis=1).astype(np.int32)
+        d, sr = self._read(filename)
+        self._account(len(d) / sr)
+        if len(d) == 0:
+            return []
+        hashes = self.fingerprint_batch([d], self.shifts)[0]
+        if self.shifts < 2 and len(hashes) == 0:
+            return []        # the reference returns [] when there are no peaks (:401-402)
+        return hashes
+
+    def ingest(self, hashtable, filename):
+        """Read a file and add it to the table (audfprint_analyze.py:430-457)."""
+        hashes = self.wavfile2hashes(filename)
+        hashtable.store(filename, hashes)
+        return self.soundfiledur, len(hashes)
+
+    # ---- parity probes -------------------------------------------------------------
+    def stft_magnitude(self, d):
+        """|STFT| (257, T) float64 — np.abs(stft.stft(...)) of the reference."""
+        a, dtype = _as_pcm(d)
+        ctx = self._configure(1)
+        T = 1 + len(a) // self.n_hop
+        out = np.empty((T, 257), np.float64)
+        ctx.check(ctx.lib.afp_stft_mag(ctx.h, a.ctypes.data, dtype, 1, len(a), out.ctypes.data, 1))
+        return out.T
+
+    def conditioned_sgram(self, d):
+        """log / mean / high-pass spectrogram (256, T) float64 (audfprint_analyze.py:280-295)."""
+        a, dtype = _as_pcm(d)
+        ctx = self._configure(1)
+        T = 1 + len(a) // self.n_hop
+        out = np.empty((T, 256), np.float64)
+        ctx.check(ctx.lib.afp_sgram(ctx.h, a.ctypes.data, dtype, 1, len(a), out.ctypes.data, 1))
+        return out.T
+
+
+# ---- precomputed-file codecs (byte-compatible, audfprint_analyze.py:460-514) --------
+HASH_FMT = '<2i'
+HASH_MAGIC = b'audfprinthashV00'
+PEAK_FMT = '<2i'
+PEAK_MAGIC = b'audfprintpeakV00'
+
+
+def _pairs_save(fname, magic, pairs):
+    arr = np.asarray(pairs, dtype='<i4').reshape(-1, 2)
+    with open(fname, 'wb') as f:
+        f.write(magic)
+        f.write(arr.tobytes())
+
+
+def _pairs_load(fname, magic, what):
+    with open(fname, 'rb') as f:
+        got = f.read(len(magic))
+        if got != magic:
+            raise IOError('%s is not a %s file (magic %s)' % (fname, what, got))
+        data = f.read()
+    n = len(data) // struct.calcsize(HASH_FMT)
+    arr = np.frombuffer(data[:n * 8], dtype='<i4').reshape(-1, 2)
+    return [(int(a), int(b)) for a, b in arr]
+
+
+def hashes_save(hashfilename, hashes):
+    _pairs_save(hashfilename, HASH_MAGIC, hashes)
+
+
+def hashes_load(hashfilename):
+    return _pairs_load(hashfilename, HASH_MAGIC, 'hash')
+
+
+def peaks_save(peakfilename, peaks):
+    _pairs_save(peakfilename, PEAK_MAGIC, peaks)
+
+
+def peaks_load(peakfilename):
+    return _pairs_load(peakfilename, PEAK_MAGIC, 'peak')

@@ -1,0 +1,143 @@
+// Internal declarations shared by the libafp translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "afp.h"
+
+#define AFP_FRAMES_PER_TILE 16      // frames one CTA pass of K1 transforms
+#define AFP_GAUSS_N (2 * AFP_NBINS + 1)
+#define AFP_GAUSS_PAD (AFP_GAUSS_N + AFP_GAUSS_N / 8 + 2)   // padded smem layout, see afp_peaks.cu
+#define AFP_NO_HASH 0xFFFFFFFFu
+
+// A device buffer that only ever grows (workspace arena member).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Per-item (file x shift) descriptor built on the host for each batch.
+struct ItemDesc {
+  int64_t sample_start;   // index of the item's first sample in the packed PCM buffer
+  int64_t nsamples;       // samples of the item (file length minus the shift offset; may be <= 0)
+  int64_t frame_base;     // first frame of the item in the batch-wide frame space
+  int32_t nframes;        // T = 1 + nsamples / 256 (0 when nsamples <= 0)
+  int32_t tile_base;      // first K1 tile of the item
+};
+
+// Per-item statistics produced by K1 + the stats kernel.
+struct ItemStats {
+  double logfloor;   // log(max|S| / 1e6)
+  double mean;       // mean of the floored log-magnitudes over 257 x T
+  int32_t allzero;   // 1 when max|S| == 0 (reference skips log/mean, audfprint_analyze.py:287-290)
+  int32_t pad;
+};
+
+struct TableDev {
+  DevBuf table, counts, hashesperid;
+  int32_t hashbits = 0, depth = 0, maxtimebits = 0;
+  int64_t nids = 0;
+  bool loaded = false;
+};
+
+struct afp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+
+  // analyzer configuration
+  afp_analyzer_params ap{};
+  bool analyzer_set = false;
+  DevBuf d_window;   // 512 doubles
+  DevBuf d_gauss;    // AFP_GAUSS_N doubles
+  DevBuf d_twid;     // FFT twiddles: W256 (256 x double2) then W512 (257 x double2)
+
+  // batch state (valid after afp_fingerprint_batch)
+  int32_t nfiles = 0, nitems = 0;
+  int64_t total_frames = 0, total_tiles = 0, total_cols = 0;
+  std::vector<ItemDesc> h_items;
+  std::vector<int64_t> h_file_col_base;   // [nfiles+1] column space of each file (= T of shift 0)
+  bool batch_valid = false;
+  int pcm_dtype = 0;
+
+  DevBuf d_pcm_stage;      // host->device staging when pcm_on_host
+  DevBuf d_items;          // ItemDesc[nitems]
+  DevBuf d_file_col_base;  // int64[nfiles+1]
+  DevBuf d_logs;           // double [total_frames][256]   log|S|, bins 0..255
+  DevBuf d_nyq;            // double [total_frames]        log|S| of the Nyquist bin
+  DevBuf d_tile_stats;     // double [total_tiles][3]      (max |S|^2, min log, sum log)
+  DevBuf d_item_stats;     // ItemStats[nitems]
+  DevBuf d_fwd_val;        // double [total_frames][maxpks]
+  DevBuf d_fwd_bin;        // uint8  [total_frames][maxpks]
+  DevBuf d_fwd_cnt;        // uint8  [total_frames]
+  DevBuf d_pk_bin;         // uint8  [total_frames][maxpks]  surviving peaks, bins ascending
+  DevBuf d_pk_cnt;         // uint8  [total_frames]
+  DevBuf d_item_scols;     // int32 [nitems]  last peak column + 1
+  DevBuf d_item_npeaks;    // int32 [nitems]
+  DevBuf d_lm;             // uint32 [total_frames][maxpks][fanout] landmark hashes (AFP_NO_HASH = none)
+  DevBuf d_col_cnt;        // int32 [total_cols]   unique hashes per (file, column); then exclusive offsets
+  DevBuf d_file_tot;       // int32 [nfiles]
+  DevBuf d_file_off;       // int64 [nfiles+1]
+  DevBuf d_hashes;         // int32 [total][2]
+  int64_t total_hashes = -1;
+  int64_t nlandmarks = -1;   // afp_landmarks_from_peaks result (rows in d_hashes)
+  DevBuf d_pk_off;         // int64 [nfiles+1] (peak fetch)
+  DevBuf d_pk_rows;        // int32 [total][2]
+  DevBuf d_tmp;            // misc
+
+  // table + matching
+  TableDev tab;
+  DevBuf d_q, d_qoff, d_hit_off, d_hits;
+  int64_t nhits = -1, hits_nq = 0;
+  DevBuf d_mscratch, d_mcounters, d_mrows, d_mrow_cnt, d_mrow_off, d_mrows_packed;
+  int32_t match_nq = 0;
+  int64_t match_total_rows = -1;
+  int32_t match_row_cap = 0;
+};
+
+#define AFP_CUDA(ctx, call)                                                        \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+      return (e__ == cudaErrorMemoryAllocation) ? AFP_ERR_NOMEM : AFP_ERR_CUDA;    \
+    }                                                                              \
+  } while (0)
+
+#define AFP_FAIL(ctx, code, msg) \
+  do {                           \
+    (ctx)->err = (msg);          \
+    return (code);               \
+  } while (0)
+
+// ---- kernel launchers (defined in the .cu files) -------------------------------
+int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out /* optional [T][257] */);
+int afp_launch_stats(afp_ctx* c);
+int afp_launch_sgram(afp_ctx* c, double* sgram_out);
+int afp_launch_peaks(afp_ctx* c);
+int afp_launch_hashes(afp_ctx* c);
+int afp_write_hashes(afp_ctx* c);
+int afp_landmarks_from_peaks_impl(afp_ctx* c, const int32_t* rows, int64_t n, int on_host, int64_t* nlm);
+int afp_compact_peaks(afp_ctx* c, int shift);
+int afp_launch_scan_i32_to_i64(afp_ctx* c, const int32_t* in, int64_t* out, int64_t n);

@@ -1,0 +1,286 @@
+"""HashTable — drop-in mirror of hash_table.HashTable with a device-resident
+copy of the bucket arrays for probing (hash_table.py:49-391).
+
+The public attributes the reference's callers read directly (`table`, `counts`,
+`names`, `hashesperid`, `params`, `hashbits`, `depth`, `maxtimebits`, `dirty`,
+`ht_version`) are plain host NumPy arrays / Python objects and remain the
+source of truth; `get_hits` (the hot method, 92 % of the reference's match
+time) runs on the GPU against a lazily refreshed device copy.  Mutation
+(`store`, `merge`, `remove`) is host bookkeeping — the "next" row §8f-1 of
+SURVEY.md — written so that it reproduces the reference's results exactly,
+including its draws from the global `random` module on bucket overflow.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import io
+import math
+import os
+import pickle
+import random
+
+import numpy as np
+
+from . import _lib
+
+HT_VERSION = 20170724
+HT_COMPAT_VERSION = 20170724
+HT_OLD_COMPAT_VERSION = 20140920
+
+
+def _bitsfor(maxval):
+    """log2 of a power of two, ValueError otherwise (hash_table.py:40-46)."""
+    bits = int(round(math.log(maxval) / math.log(2)))
+    if maxval != (1 << bits):
+        raise ValueError("maxval must be a power of 2, not %d" % maxval)
+    return bits
+
+
+class _RefUnpickler(pickle.Unpickler):
+    """Reads databases pickled by the reference (class path hash_table.HashTable)."""
+
+    def find_class(self, module, name):
+        if name == "HashTable" and module in ("hash_table", "audfprint.hash_table", __name__):
+            return HashTable
+        return super().find_class(module, name)
+
+
+class HashTable(object):
+    """Fixed-array hash table of (id, time) entries keyed by landmark hash."""
+
+    def __init__(self, filename=None, hashbits=20, depth=100, maxtime=16384, device=None):
+        self.device = device
+        self._dev_stamp = None       # identity of the arrays last uploaded
+        self._version = 0            # bumped on every mutation
+        if filename is not None:
+            self.load(filename)
+        else:
+            self.hashbits = hashbits
+            self.depth = depth
+            self.maxtimebits = _bitsfor(maxtime)
+            size = 2 ** hashbits
+            self.table = np.zeros((size, depth), dtype=np.uint32)
+            self.counts = np.zeros(size, dtype=np.int32)
+            self.names = []
+            self.hashesperid = np.zeros(0, np.uint32)
+            self.params = {}
+            self.ht_version = HT_VERSION
+            self.dirty = True
+
+    # ---- pickling: only plain host state travels (reference pickles the object) ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_dev_stamp", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._dev_stamp = None
+        self.__dict__.setdefault("_version", 0)
+        self.__dict__.setdefault("device", None)
+
+    def _touch(self):
+        self._version += 1
+        self.dirty = True
+
+    def reset(self):
+        """Empty the table, keep the geometry (hash_table.py:83-89)."""
+        self.table[:, :] = 0
+        self.counts[:] = 0
+        self.names = []
+        self.hashesperid = np.zeros(0, np.uint32)
+        self._touch()
+
+    # ---- mutation (host) ---------------------------------------------------------
+    def store(self, name, timehashpairs):
+        """Insert (time, hash) pairs under `name` (hash_table.py:91-138).
+
+        Same sequential semantics as the reference, evaluated in two parts: rows
+        that land below `depth` are written with one vectorised scatter; rows
+        that hit a full bucket are replayed one by one, drawing
+        random.randint(0, count) in the original order, so a table built here
+        equals one built by the reference from the same RNG state."""
+        id_ = self.name_to_id(name, add_if_missing=True)
+        pairs = np.asarray(timehashpairs, dtype=np.int64).reshape(-1, 2)
+        n = pairs.shape[0]
+        if n:
+            hmask = (1 << self.hashbits) - 1
+            tmask = (1 << self.maxtimebits) - 1
+            if (id_ + 2) << self.maxtimebits > (1 << 32):
+                raise OverflowError("id %d does not fit in %d id bits" % (id_, 32 - self.maxtimebits))
+            h = pairs[:, 1] & hmask
+            vals = (((id_ + 1) << self.maxtimebits) + (pairs[:, 0] & tmask)).astype(np.uint32)
+            # occurrence index of every row among equal hashes, in call order
+            order = np.argsort(h, kind="stable")
+            hs = h[order]
+            first = np.r_[True, hs[1:] != hs[:-1]]
+            grp_start = np.maximum.accumulate(np.where(first, np.arange(n), 0))
+            occ = np.empty(n, np.int64)
+            occ[order] = np.arange(n) - grp_start
+            pos = self.counts[h].astype(np.int64) + occ
+            direct = pos < self.depth
+            self.table[h[direct], pos[direct]] = vals[direct]
+            for i in np.nonzero(~direct)[0]:
+                slot = random.randint(0, int(pos[i]))
+                if slot < self.depth:
+                    self.table[h[i], slot] = vals[i]
+            np.add.at(self.counts, h, 1)
+        self.hashesperid[id_] += n
+        self._touch()
+
+    def merge(self, ht):
+        """Merge another table, ids offset by our size (hash_table.py:291-323)."""
+        assert self.maxtimebits == ht.maxtimebits
+        ncurrent = len(self.names)
+        self.names += ht.names
+        self.hashesperid = np.append(self.hashesperid, ht.hashesperid)
+        idoffset = (1 << self.maxtimebits) * ncurrent
+        for hash_ in np.nonzero(ht.counts)[0]:
+            allvals = np.r_[self.table[hash_, :self.counts[hash_]],
+                            ht.table[hash_, :ht.counts[hash_]] + idoffset]
+            if len(allvals) > self.depth:
+                somevals = np.random.permutation(allvals)[:self.depth]
+                self.table[hash_, ] = somevals
+                self.counts[hash_] += ht.counts[hash_]
+            else:
+                self.table[hash_, :len(allvals)] = allvals
+                self.counts[hash_] = len(allvals)
+        self._touch()
+
+    def name_to_id(self, name, add_if_missing=False):
+        """Name -> id, optionally allocating (hash_table.py:325-345)."""
+        if isinstance(name, (str, bytes)):
+            if name not in self.names:
+                if not add_if_missing:
+                    raise ValueError("name " + str(name) + " not found")
+                try:
+                    id_ = self.names.index(None)
+                    self.names[id_] = name
+                    self.hashesperid[id_] = 0
+                except ValueError:
+                    self.names.append(name)
+                    self.hashesperid = np.append(self.hashesperid, [0]).astype(np.uint32)
+            id_ = self.names.index(name)
+        else:
+            id_ = name
+        return id_
+
+    def remove(self, name):
+        """Drop every entry of `name` (hash_table.py:347-367)."""
+        id_ = self.name_to_id(name)
+        mine = (self.table >> np.uint32(self.maxtimebits)) == id_ + 1
+        removed = 0
+        for hash_ in np.nonzero(np.max(mine, axis=1))[0]:
+            n = min(self.depth, int(self.counts[hash_]))
+            row = self.table[hash_, :n]
+            keep = row[~mine[hash_, :n]]
+            self.table[hash_] = 0
+            self.table[hash_, :len(keep)] = keep
+            self.counts[hash_] = len(keep)
+            removed += int(np.sum(mine[hash_]))
+        self.names[id_] = None
+        self.hashesperid[id_] = 0
+        self._touch()
+        print("Removed", name, "(", removed, "hashes).")
+
+    def retrieve(self, name):
+        """(time, hash) pairs stored for `name` (hash_table.py:369-385)."""
+        id_ = self.name_to_id(name)
+        tmask = (1 << self.maxtimebits) - 1
+        valid = np.arange(self.depth)[None, :] < np.minimum(self.depth, self.counts)[:, None]
+        hit = ((self.table >> np.uint32(self.maxtimebits)) == id_ + 1) & valid
+        hs, slots = np.nonzero(hit)
+        out = np.zeros((len(hs), 2), dtype=np.int32)
+        out[:, 0] = self.table[hs, slots] & tmask
+        out[:, 1] = hs
+        return out
+
+    def list(self, print_fn=None):
+        """Print every known item (hash_table.py:387-391)."""
+        if not print_fn:
+            print_fn = print
+        for name, count in zip(self.names, self.hashesperid):
+            if name:
+                print_fn(name + " (" + str(count) + " hashes)")
+
+    def totalhashes(self):
+        return np.sum(self.counts)
+
+    # ---- persistence (gzip pickle, hash_table.py:178-246) -------------------------------
+    def save(self, name, params=None, file_object=None):
+        if params:
+            for key in params:
+                self.params[key] = params[key]
+        f = file_object if file_object else gzip.open(name, 'wb')
+        pickle.dump(self, f, pickle.HIGHEST_PROTOCOL)
+        if not file_object:
+            f.close()
+        self.dirty = False
+        nhashes = int(np.sum(self.counts))
+        dropped = nhashes - int(np.sum(np.minimum(self.depth, self.counts)))
+        print("Saved fprints for", sum(n is not None for n in self.names),
+              "files (", nhashes, "hashes) to", name,
+              "(%.2f%% dropped)" % (100.0 * dropped / max(1, nhashes)))
+
+    def load(self, name):
+        ext = os.path.splitext(name)[1]
+        if ext == '.mat':
+            raise NotImplementedError("Matlab .mat databases (hash_table.py:248-285) are not supported")
+        self.load_pkl(name)
+        nhashes = int(np.sum(self.counts))
+        dropped = nhashes - int(np.sum(np.minimum(self.depth, self.counts)))
+        print("Read fprints for", sum(n is not None for n in self.names),
+              "files (", nhashes, "hashes) from", name,
+              "(%.2f%% dropped)" % (100.0 * dropped / max(1, nhashes)))
+
+    def load_pkl(self, name, file_object=None):
+        f = file_object if file_object else gzip.open(name, 'rb')
+        temp = _RefUnpickler(io.BytesIO(f.read()), encoding='latin1').load()
+        if not file_object:
+            f.close()
+        if temp.ht_version < HT_OLD_COMPAT_VERSION:
+            raise ValueError('Version of ' + name + ' is ' + str(temp.ht_version)
+                             + ' which is not at least ' + str(HT_OLD_COMPAT_VERSION))
+        self.hashbits = temp.hashbits
+        self.depth = temp.depth
+        self.maxtimebits = temp.maxtimebits if hasattr(temp, 'maxtimebits') else _bitsfor(temp.maxtime)
+        table = temp.table
+        if temp.ht_version < HT_COMPAT_VERSION:
+            print("Loading database version", temp.ht_version, "in compatibility mode.")
+            table = table + np.array(1 << self.maxtimebits).astype(np.uint32) * (table != 0)
+        self.table = np.ascontiguousarray(table, dtype=np.uint32)
+        self.ht_version = HT_VERSION
+        self.counts = np.ascontiguousarray(temp.counts, dtype=np.int32)
+        self.names = temp.names
+        self.hashesperid = np.array(temp.hashesperid).astype(np.uint32)
+        self.params = temp.params
+        self.dirty = False
+        self._version = getattr(self, "_version", 0) + 1
+        self._dev_stamp = None
+
+    # ---- device copy + probe --------------------------------------------------------
+    def _sync_device(self):
+        """Upload table/counts/hashesperid if they changed since the last upload."""
+        ctx = _lib.context(self.device)
+        stamp = (id(self), self._version, id(self.table), id(self.counts))
+        if ctx.table_key != stamp:
+            table = np.ascontiguousarray(self.table, dtype=np.uint32)
+            counts = np.ascontiguousarray(self.counts, dtype=np.int32)
+            hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
+            ctx.check(ctx.lib.afp_table_upload(ctx.h, table.ctypes.data, counts.ctypes.data, int(self.hashbits),
+                                               int(self.depth), int(self.maxtimebits),
+                                               hpi.ctypes.data if len(hpi) else None, len(hpi), 1))
+            ctx.table_key = stamp
+        return ctx
+
+    def get_hits(self, hashes):
+        """[time, hash] rows -> int32 (nhits,4) [id, dtime, hash, time] rows in
+        (query row, slot) order (hash_table.py:150-176)."""
+        q = np.ascontiguousarray(np.asarray(hashes, dtype=np.int32).reshape(-1, 2))
+        ctx = self._sync_device()
+        n = C.c_int64(0)
+        ctx.check(ctx.lib.afp_get_hits(ctx.h, q.ctypes.data if len(q) else None, len(q), 1, C.byref(n)))
+        hits = np.empty((int(n.value), 4), np.int32)
+        ctx.check(ctx.lib.afp_fetch_hits(ctx.h, hits.ctypes.data if len(hits) else None, 1))
+        return hits

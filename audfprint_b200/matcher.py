@@ -1,0 +1,125 @@
+"""Matcher — drop-in mirror of audfprint_match.Matcher (audfprint_match.py:93-420)
+whose probe / candidate ranking / time-offset histogramming run in libafp.so.
+
+Host code keeps only what the reference does after the hot part: the final
+`results[(-results[:, 1]).argsort(),]` ordering (the very NumPy call of
+audfprint_match.py:335, so equal counts come out as they do in the reference on
+the same machine), `max_returns` truncation and message formatting.
+
+Not provided (optional second-wave flags): exact_count,
+find_time_range, illustrate — they raise NotImplementedError when set.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+
+
+class Matcher(object):
+    """Provide matching for audfprint fingerprint queries to hash table."""
+
+    def __init__(self):
+        # defaults of audfprint_match.py:96-122
+        self.window = 1
+        self.threshcount = 5
+        self.max_returns = 1
+        self.search_depth = 100
+        self.sort_by_time = False
+        self.verbose = False
+        self.illustrate = False
+        self.exact_count = False
+        self.find_time_range = False
+        self.time_quantile = 0.02
+        self.illustrate_hpf = False
+        self.max_alignments_per_id = 100
+
+    def _params(self):
+        if self.exact_count or self.find_time_range or self.illustrate:
+            raise NotImplementedError("exact_count / find_time_range / illustrate are not implemented "
+                                      "on the CUDA path (SURVEY.md §8f-4)")
+        return _lib.MatcherParams(int(self.window), int(self.threshcount), int(self.search_depth),
+                                  int(self.max_alignments_per_id))
+
+    def match_batch(self, ht, queries, sort=True):
+        """Match many queries in one device call.
+
+        queries  list of int32 (nq_i, 2) [time, hash] arrays (or one packed
+                 (rows, offsets) tuple)
+        returns  list of int32 (R_i, 7) rows [id, count, dtime, raw, rank, 0, 0],
+                 sorted by count descending like match_hashes."""
+        if isinstance(queries, tuple):
+            packed, qoff = queries
+            packed = np.ascontiguousarray(packed, dtype=np.int32).reshape(-1, 2)
+            qoff = np.ascontiguousarray(qoff, dtype=np.int64)
+        else:
+            arrs = [np.asarray(q, dtype=np.int32).reshape(-1, 2) for q in queries]
+            qoff = np.zeros(len(arrs) + 1, np.int64)
+            if arrs:
+                qoff[1:] = np.cumsum([len(a) for a in arrs])
+            packed = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros((0, 2), np.int32)
+        nq = len(qoff) - 1
+        p = self._params()
+        ctx = ht._sync_device()
+        total = C.c_int64(0)
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
+                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
+        rows = np.empty((int(total.value), 7), np.int32)
+        roff = np.zeros(nq + 1, np.int64)
+        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        out = []
+        for i in range(nq):
+            r = rows[roff[i]:roff[i + 1]]
+            if sort:
+                r = r[(-r[:, 1]).argsort(), ]        # audfprint_match.py:335
+            out.append(r)
+        return out
+
+    def match_hashes(self, ht, hashes, hashesfor=None):
+        """Query hashes -> rows (id, filteredmatches, timoffs, rawmatches, origrank,
+        mintime, maxtime), best first (audfprint_match.py:314-352)."""
+        if hashesfor is not None:
+            raise NotImplementedError("hashesfor needs _unique_match_hashes (SURVEY.md §8f-4)")
+        q = np.asarray(hashes, dtype=np.int32).reshape(-1, 2)
+        return self.match_batch(ht, [q])[0]
+
+    def match_file(self, analyzer, ht, filename, number=None):
+        """Read, fingerprint and match one file (audfprint_match.py:354-379)."""
+        q_hashes = analyzer.wavfile2hashes(filename)
+        if len(q_hashes) == 0:
+            durd = 0.0
+        else:
+            durd = analyzer.n_hop * q_hashes[-1][0] / analyzer.target_sr
+        if self.verbose:
+            numberstring = "#%d" % number if number is not None else ""
+            print(time.ctime(), "Analyzed", numberstring, filename, "of", ('%.3f' % durd), "s "
+                  "to", len(q_hashes), "hashes")
+        rslts = self.match_hashes(ht, q_hashes)
+        if self.sort_by_time:
+            rslts = rslts[(-rslts[:, 2]).argsort(), :]
+        return rslts[:self.max_returns, :], durd, len(q_hashes)
+
+    def file_match_to_msgs(self, analyzer, ht, qry, number=None):
+        """Match one file and format the reference's report lines
+        (audfprint_match.py:381-420)."""
+        rslts, dur, nhash = self.match_file(analyzer, ht, qry, number)
+        t_hop = analyzer.n_hop / analyzer.target_sr
+        qrymsg = qry + (' %.1f ' % dur) + "sec " + str(nhash) + " raw hashes" if self.verbose else qry
+        msgrslt = []
+        if len(rslts) == 0:
+            msgrslt.append("NOMATCH " + qrymsg if self.verbose else qrymsg + "\t")
+        else:
+            for (tophitid, nhashaligned, aligntime, nhashraw, rank, min_time, max_time) in rslts:
+                if self.verbose:
+                    msg = "Matched {:s} as {:s} at {:6.1f} s".format(qrymsg, ht.names[tophitid],
+                                                                    aligntime * t_hop)
+                    msg += (" with {:5d} of {:5d} common hashes at rank {:2d}").format(
+                        nhashaligned, nhashraw, rank)
+                    msgrslt.append(msg)
+                else:
+                    msgrslt.append(qrymsg + "\t" + ht.names[tophitid])
+        return msgrslt

@@ -1,0 +1,176 @@
+/*
+ * afp.h — C ABI of libafp.so, the sm_100a landmark-fingerprint engine.
+ *
+ * This is the drop-in boundary for the ONE hot path SURVEY.md §8 scopes.  The
+ * reference (dpwe/audfprint @ cb03ba99) is pure Python and has no FFI of its
+ * own; the "operator API" a replacement must honour is the method set of its
+ * three domain classes.  Each entry point below names the
+ * reference method(s) it stands behind.  The Python mirror of those classes
+ * (audfprint_b200/{analyzer,hash_table,matcher}.py) reaches these symbols
+ * through ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, negative = afp_status;
+ *     afp_last_error() gives the message.  No exception crosses the ABI.
+ *   - plain pointers and sizes only.  A pointer argument named *_dev / with an
+ *     `on_host` flag of 0 is a DEVICE pointer (e.g. torch.Tensor.data_ptr());
+ *     with on_host = 1 it is a HOST pointer and the library does the
+ *     host<->device copy itself on its stream.
+ *   - buffers are caller-owned; the context owns only its internal workspace.
+ *   - one context per process per GPU; calls are asynchronous on the context's
+ *     stream except where a result count must be returned to the host.
+ *   - there is no CPU fallback: every call needs a CUDA device.
+ */
+#ifndef AFP_H_
+#define AFP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFP_ABI_VERSION 1
+
+typedef struct afp_ctx afp_ctx;
+
+typedef enum {
+  AFP_OK = 0,
+  AFP_ERR_CUDA = -1,        /* a CUDA runtime call failed                       */
+  AFP_ERR_INVALID = -2,     /* bad argument (maps to ValueError)               */
+  AFP_ERR_UNSUPPORTED = -3, /* parameter outside the compiled limits           */
+  AFP_ERR_NOMEM = -4,       /* device workspace allocation failed              */
+  AFP_ERR_STATE = -5        /* call order violated (e.g. fetch before compute) */
+} afp_status;
+
+enum { AFP_PCM_I16 = 0, AFP_PCM_F32 = 1 };
+
+/* compiled limits */
+#define AFP_N_FFT 512
+#define AFP_N_HOP 256
+#define AFP_NBINS 256           /* bins kept (Nyquist row dropped)           */
+#define AFP_MAX_PKS 16          /* maxpksperframe upper bound                */
+#define AFP_MAX_MERGE 256       /* shifts*maxpksperframe*maxpairsperpeak cap */
+
+/* Analyzer attributes (audfprint_analyze.py:125-151; set by the CLI at
+ * audfprint.py:285-298). */
+typedef struct {
+  double a_dec;            /* decay per frame, audfprint_analyze.py:277          */
+  double hpf_pole;         /* HPF_POLE, audfprint_analyze.py:60                  */
+  int32_t maxpksperframe;  /* Analyzer.maxpksperframe (5)                        */
+  int32_t maxpairsperpeak; /* Analyzer.maxpairsperpeak (3, --fanout)             */
+  int32_t targetdf;        /* 31                                                 */
+  int32_t mindt;           /* 2                                                  */
+  int32_t targetdt;        /* 63                                                 */
+  int32_t shifts;          /* Analyzer.shifts (1; 4 for match)                   */
+} afp_analyzer_params;
+
+/* Matcher attributes (audfprint_match.py:96-122). */
+typedef struct {
+  int32_t window;                /* Matcher.window                    */
+  int32_t threshcount;           /* Matcher.threshcount               */
+  int32_t search_depth;          /* Matcher.search_depth              */
+  int32_t max_alignments_per_id; /* Matcher.max_alignments_per_id     */
+} afp_matcher_params;
+
+/* ---- context --------------------------------------------------------------- */
+int afp_abi_version(void);
+int afp_create(afp_ctx** out, int device);
+void afp_destroy(afp_ctx* ctx);
+const char* afp_last_error(afp_ctx* ctx);
+/* Use the caller's CUDA stream (cudaStream_t as void*); NULL = library-owned. */
+int afp_set_stream(afp_ctx* ctx, void* cuda_stream);
+int afp_sync(afp_ctx* ctx);
+/* Number of kernel launches issued by this context so far (bench accounting). */
+int64_t afp_launch_count(afp_ctx* ctx);
+
+/* ---- Analyzer --------------------------------------------------------------
+ * Replaces stft.stft (stft.py:62-94) + Analyzer.find_peaks
+ * (audfprint_analyze.py:255-308) + peaks2landmarks (:310-343) +
+ * landmarks2hashes (:81-96) + the shift/dedupe logic of wavfile2hashes
+ * (:401-422).
+ *
+ * `window` is the 512-point analysis window (np.hanning(514)[1:-1]) and
+ * `gauss` the 513-point spreading table exp(-0.5*((j-256)/f_sd)^2)
+ * (audfprint_analyze.py:187-192), both computed by the host so that they are
+ * the very doubles the reference multiplies by.  Either may be NULL, in which
+ * case the library computes it with libm for f_sd. */
+int afp_set_analyzer(afp_ctx* ctx, const afp_analyzer_params* p,
+                     const double* window, const double* gauss, double f_sd);
+
+/* Fingerprint a batch of files held as one packed PCM buffer.
+ *   pcm            packed samples of all files (int16 or float32)
+ *   sample_offsets HOST array [nfiles+1]; file i starts at pcm[off[i]]
+ *   sample_lengths HOST array [nfiles] or NULL; NULL means off[i+1]-off[i].
+ *                  Explicit lengths let the caller pad each file to a 16-byte
+ *                  boundary, which is what lets K1 stage interior tiles with
+ *                  TMA bulk copies (unaligned files take the scalar-load path).
+ * On return the hashes of every file are in the context workspace;
+ * *total_hashes (may be NULL -> no host sync) receives their number. */
+int afp_fingerprint_batch(afp_ctx* ctx, const void* pcm, int pcm_dtype, int pcm_on_host,
+                          int32_t nfiles, const int64_t* sample_offsets,
+                          const int64_t* sample_lengths, int64_t* total_hashes);
+/* Copy the result of the last afp_fingerprint_batch: `rows` int32 [total][2]
+ * = (time, hash) sorted by (time, hash) per file (audfprint_analyze.py:415-421),
+ * `row_offsets` HOST int64 [nfiles+1].  Either may be NULL. */
+int afp_fetch_hashes(afp_ctx* ctx, int32_t* rows, int rows_on_host, int64_t* row_offsets);
+/* Peaks of one shift of the last batch (Analyzer.find_peaks / wavfile2peaks):
+ * `rows` int32 [total][2] = (col, bin) column-major, bins ascending
+ * (audfprint_analyze.py:303-308); `row_offsets` HOST int64 [nfiles+1].
+ * Call with rows = NULL first to obtain the offsets/total. */
+int afp_fetch_peaks(afp_ctx* ctx, int32_t shift, int32_t* rows, int rows_on_host,
+                    int64_t* row_offsets);
+
+/* Analyzer.peaks2landmarks (audfprint_analyze.py:310-343) on an explicit peak
+ * list (e.g. read from a precomputed .afpk file): `peak_rows` int32 [n][2] =
+ * (col, bin), column-major with bins ascending.  Result (fetch): int32 [L][4] =
+ * (col, bin1, bin2, dt) in the reference's generation order.  Invalidates the
+ * last fingerprint batch. */
+int afp_landmarks_from_peaks(afp_ctx* ctx, const int32_t* peak_rows, int64_t npeaks, int on_host,
+                             int64_t* nlandmarks);
+int afp_fetch_landmarks(afp_ctx* ctx, int32_t* rows, int rows_on_host);
+
+/* Exposed for the STFT parity check (north_star: magnitudes within 1e-5):
+ * |STFT| of one signal, float64 [T][257] (frame-major), T = 1 + n/256.
+ * Replaces np.abs(stft.stft(d, 512, 256, window)) (audfprint_analyze.py:280). */
+int afp_stft_mag(afp_ctx* ctx, const void* pcm, int pcm_dtype, int pcm_on_host, int64_t n,
+                 double* mag, int mag_on_host);
+/* Conditioned spectrogram log/mean/HPF of one signal, float64 [T][256]
+ * (audfprint_analyze.py:280-295). */
+int afp_sgram(afp_ctx* ctx, const void* pcm, int pcm_dtype, int pcm_on_host, int64_t n,
+              double* sgram, int sgram_on_host);
+
+/* ---- HashTable --------------------------------------------------------------
+ * Device-resident copy of HashTable.table / counts / hashesperid
+ * (hash_table.py:59-81).  `table` uint32 [2^hashbits][depth] row-major,
+ * `counts` int32 [2^hashbits], `hashesperid` uint32 [nids]. */
+int afp_table_upload(afp_ctx* ctx, const uint32_t* table, const int32_t* counts,
+                     int32_t hashbits, int32_t depth, int32_t maxtimebits,
+                     const uint32_t* hashesperid, int64_t nids, int on_host);
+/* Keep only ids in [id_lo, id_hi) of the uploaded table (sharded table,
+ * SURVEY.md §8e); bucket-slot order is preserved. */
+int afp_table_restrict_ids(afp_ctx* ctx, int64_t id_lo, int64_t id_hi);
+/* HashTable.get_hits (hash_table.py:150-176): query rows int32 [nq][2] =
+ * (time, hash) -> hits int32 [nhits][4] = (id, dtime, hash, qtime) in
+ * (query row, slot) order.  Two steps: count, then fetch. */
+int afp_get_hits(afp_ctx* ctx, const int32_t* q_rows, int64_t nq, int q_on_host,
+                 int64_t* nhits);
+int afp_fetch_hits(afp_ctx* ctx, int32_t* hits, int hits_on_host);
+
+/* ---- Matcher ----------------------------------------------------------------
+ * Matcher.match_hashes (audfprint_match.py:314-352) for a batch of queries:
+ * get_hits -> _best_count_ids (:124-147) -> _approx_match_counts (:241-312).
+ *   q_rows     int32 [sum nq][2] (time, hash) of all queries, packed
+ *   q_offsets  HOST int64 [nqueries+1]
+ * Result rows int32 [R][7] = (id, count, dtime, raw, rank, 0, 0) per query in
+ * candidate-rank order; the final sort by count (:335) is left to the host
+ * mirror so that it is the very numpy call the reference makes. */
+int afp_match_batch(afp_ctx* ctx, const int32_t* q_rows, int q_on_host, int32_t nqueries,
+                    const int64_t* q_offsets, const afp_matcher_params* p,
+                    int64_t* total_rows);
+int afp_fetch_match_rows(afp_ctx* ctx, int32_t* rows, int rows_on_host, int64_t* row_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFP_H_ */

@@ -1,0 +1,120 @@
+"""CPU: the C-ABI library loads and exports every symbol include/afp.h declares;
+host-side logic (packing, codecs, table bookkeeping) without any compute call."""
+import os
+import pickle
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from audfprint_b200 import _lib, HashTable, Analyzer, Matcher
+from audfprint_b200 import analyzer as an_mod
+from oracle import afp_oracle as orc
+from tests import cases
+from tests.conftest import expand_table
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    entry.build()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load(check_symbols=True)
+    syms = _lib.header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.afp_abi_version() == 1
+
+
+def test_fft_index_algebra_host_check():
+    out = subprocess.run([os.path.join(entry.ROOT, "build", "fft_host_check")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.AfpError):
+        Analyzer().find_peaks(np.zeros(1000, np.float32), 11025)
+
+
+@pytest.mark.parametrize("db", ["db", "db2"])
+def test_store_matches_reference_table(golden_match, db):
+    table, counts, hashbits, depth, mtb, hpi = expand_table(golden_match, db)
+    random.seed(1234)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    for i in range(cases.DB_NTRACKS):
+        ht.store("track%d" % i, golden_match["track%d/hashes" % i])
+    assert np.array_equal(ht.counts, counts)
+    assert np.array_equal(ht.table, table)
+    assert np.array_equal(ht.hashesperid, hpi)
+    assert ht.names[3] == "track3" and ht.dirty
+
+
+def test_table_bookkeeping_roundtrip(tmp_path, golden_match):
+    ht = HashTable(hashbits=12, depth=6, maxtime=1 << 10)
+    random.seed(5)
+    h0 = golden_match["track0/hashes"]
+    h1 = golden_match["track1/hashes"]
+    ht.store("a", h0)
+    ht.store("b", h1)
+    got = ht.retrieve("b")
+    # retrieve returns what survived (bucket overflow drops some); all are real rows of b
+    want = {(int(t) & 1023, int(h) & 4095) for t, h in h1}
+    assert len(got) > 0 and {(int(t), int(h)) for t, h in got} <= want
+    fn = str(tmp_path / "db.pklz")
+    ht.save(fn)
+    ht2 = HashTable(fn)
+    assert np.array_equal(ht2.table, ht.table) and np.array_equal(ht2.counts, ht.counts)
+    assert ht2.names == ["a", "b"] and not ht2.dirty
+    ht2.remove("a")
+    assert ht2.names[0] is None and ht2.hashesperid[0] == 0
+    assert not np.any((ht2.table >> 10) == 1)
+    with pytest.raises(ValueError):
+        ht2.name_to_id("zzz")
+    with pytest.raises(ValueError):
+        HashTable(maxtime=1000)
+    other = HashTable(hashbits=12, depth=6, maxtime=1 << 10)
+    other.store("c", h0[:50])
+    n_before = len(ht2.names)
+    ht2.merge(other)
+    assert ht2.names[n_before] == "c"
+    p = pickle.loads(pickle.dumps(ht))
+    assert np.array_equal(p.table, ht.table)
+
+
+def test_codecs_are_byte_compatible(tmp_path):
+    rows = [(0, 5), (3, 1048575), (70000, 12)]
+    fn = str(tmp_path / "x.afpt")
+    an_mod.hashes_save(fn, rows)
+    raw = open(fn, "rb").read()
+    assert raw[:16] == b"audfprinthashV00" and len(raw) == 16 + 8 * 3
+    assert an_mod.hashes_load(fn) == rows
+    fk = str(tmp_path / "x.afpk")
+    an_mod.peaks_save(fk, rows)
+    assert open(fk, "rb").read()[:16] == b"audfprintpeakV00"
+    assert an_mod.peaks_load(fk) == rows
+    with pytest.raises(IOError):
+        an_mod.hashes_load(fk)
+
+
+def test_hash_packing_matches_oracle():
+    lms = [(5, 10, 40, 2), (7, 255, 225, 62), (9, 0, 30, 33)]
+    assert np.array_equal(an_mod.landmarks2hashes(lms), orc.landmarks_to_hashes(lms))
+    assert an_mod.hashes2landmarks(an_mod.landmarks2hashes(lms)) == lms
+    assert an_mod.landmarks2hashes([]).shape == (0, 2)
+
+
+def test_objects_pickle_without_device_state():
+    a = pickle.loads(pickle.dumps(Analyzer(density=70.0)))
+    assert a.density == 70.0 and a.shifts == 1 and a.maxpksperframe == 5
+    m = pickle.loads(pickle.dumps(Matcher()))
+    assert m.window == 1 and m.threshcount == 5
+    m.exact_count = True
+    with pytest.raises(NotImplementedError):
+        m._params()

@@ -1,0 +1,190 @@
+"""GPU: parity of the CUDA path (through the C ABI / the class mirror) against
+the live-reference goldens and against the oracle on fresh seeded inputs.
+Bar: hashes, peaks, hits and match rows bit-exact; STFT magnitudes within
+1e-5 relative (north_star), in practice ~1e-13."""
+import numpy as np
+import pytest
+
+from audfprint_b200 import Analyzer, HashTable, Matcher
+from audfprint_b200.synth import synth_track, synth_query, pcm_to_float
+from oracle import afp_oracle as orc
+from tests import cases
+from tests.conftest import expand_table
+
+pytestmark = pytest.mark.gpu
+SG_STRIDE = 97
+STFT_RTOL = 1e-5          # tolerance stated by BASELINE.json north_star
+
+
+def rows2(x):
+    return np.asarray(x, np.int32).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("name,seed,secs", cases.NOISE_CASES)
+def test_noise_cases_vs_reference_golden(golden_fp, name, seed, secs):
+    pcm = synth_track(seed, secs)
+    an = Analyzer()
+    mag = an.stft_magnitude(pcm)
+    want_mag = golden_fp[name + "/mag_cols"]
+    got_mag = mag[:, ::SG_STRIDE]
+    scale = np.max(want_mag)
+    assert np.max(np.abs(got_mag - want_mag)) <= STFT_RTOL * scale
+    assert np.max(np.abs(got_mag - want_mag)) <= 1e-11 * scale      # what FP64 actually achieves
+    sg = an.conditioned_sgram(pcm)
+    assert np.max(np.abs(sg[:, ::SG_STRIDE] - golden_fp[name + "/sgram_cols"])) < 1e-9
+    pk = an.find_peaks(pcm_to_float(pcm), 11025)
+    assert np.array_equal(rows2(pk), golden_fp[name + "/peaks"])
+    lm = an.peaks2landmarks(pk)
+    assert np.array_equal(np.asarray(lm, np.int32).reshape(-1, 4), golden_fp[name + "/landmarks"])
+    h1 = an.fingerprint_batch([pcm])[0]
+    assert np.array_equal(h1, golden_fp[name + "/wf2h_s1"])
+    an.shifts = 4
+    h4 = an.fingerprint_batch([pcm])[0]
+    assert np.array_equal(h4, golden_fp[name + "/wf2h_s4"])
+
+
+# 'impulses' (single-sample clicks over exact digital silence) has a perfectly
+# flat spectrum in every non-silent frame: every |X[k]| ties in exact arithmetic,
+# so the reference's peak positions there are decided by pocketfft's rounding
+# noise (~1e-16) and are not reproducible by ANY other FFT (DESIGN.md
+# "Precision and ties").  It is checked for structure, not bit-equality.
+NOISE_DECIDED = {"impulses"}
+
+
+def test_rounding_noise_decided_input_is_structurally_sane(golden_fp):
+    pcm = cases.adversarial_pcm("impulses")
+    an = Analyzer()
+    got = rows2(an.find_peaks(pcm, 11025))
+    want = golden_fp["impulses/peaks"]
+    click_frames = set()
+    for pos in range(0, len(pcm), 3001):
+        for f in (pos // 256, pos // 256 + 1):
+            click_frames.update((f - 1, f, f + 1))
+    assert len(got) > 0 and set(got[:, 0].tolist()) <= click_frames
+    assert set(want[:, 0].tolist()) <= click_frames
+    assert abs(len(got) - len(want)) <= 0.5 * len(want)
+
+
+@pytest.mark.parametrize("name", [n for n in cases.ADVERSARIAL if n not in NOISE_DECIDED])
+def test_adversarial_cases_vs_reference_golden(golden_fp, name):
+    pcm = cases.adversarial_pcm(name)
+    an = Analyzer()
+    assert np.array_equal(rows2(an.find_peaks(pcm, 11025)), golden_fp[name + "/peaks"])
+    assert np.array_equal(an.fingerprint_batch([pcm])[0], golden_fp[name + "/wf2h_s1"])
+    an.shifts = 4
+    assert np.array_equal(an.fingerprint_batch([pcm])[0], golden_fp[name + "/wf2h_s4"])
+    # float32 input path gives the same answer as int16
+    assert np.array_equal(an.fingerprint_batch([pcm_to_float(pcm)])[0], golden_fp[name + "/wf2h_s4"])
+
+
+@pytest.mark.parametrize("name,seed,secs,dens,fan", cases.DENSITY_CASES)
+def test_density_cases_vs_reference_golden(golden_fp, name, seed, secs, dens, fan):
+    pcm = synth_track(seed, secs)
+    an = Analyzer(density=dens)
+    an.maxpairsperpeak = fan
+    assert np.array_equal(rows2(an.find_peaks(pcm, 11025)), golden_fp[name + "/peaks"])
+    assert np.array_equal(an.fingerprint_batch([pcm])[0], golden_fp[name + "/wf2h_s1"])
+
+
+def test_ragged_batch_vs_oracle():
+    """Mixed lengths (incl. empty and sub-frame files) in one packed batch."""
+    rng = np.random.default_rng(11)
+    lens = [0, 1, 255, 256, 257, 4000, 33075, 50001, 110250, 77777, 12, 99999]
+    sigs = [synth_track(900 + i, 12.0)[:n].copy() for i, n in enumerate(lens)]
+    for shifts in (1, 4):
+        an = Analyzer()
+        an.shifts = shifts
+        got = an.fingerprint_batch(sigs)
+        for s, g in zip(sigs, got):
+            want = orc.fingerprint(pcm_to_float(s), shifts=shifts)
+            assert np.array_equal(g, want), (len(s), shifts)
+    assert rng is not None
+
+
+def test_fresh_seeds_vs_oracle():
+    sigs = [synth_track(2000 + i, 15.0) for i in range(24)]
+    an = Analyzer()
+    got = an.fingerprint_batch(sigs)
+    nh = 0
+    for s, g in zip(sigs, got):
+        assert np.array_equal(g, orc.fingerprint(pcm_to_float(s)))
+        nh += len(g)
+    assert nh > 5000
+
+
+def test_empty_and_errors():
+    an = Analyzer()
+    assert an.find_peaks(np.zeros(0, np.float32), 11025) == []
+    assert an.fingerprint_batch([]) == []
+    assert an.peaks2landmarks([]) == []
+    an.maxpksperframe = 99
+    with pytest.raises(Exception):
+        an.find_peaks(np.zeros(1000, np.float32), 11025)
+
+
+@pytest.mark.parametrize("db", ["db", "db2"])
+def test_get_hits_and_match_vs_reference_golden(golden_match, db):
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    ht.names = ["track%d" % i for i in range(cases.DB_NTRACKS)]
+    nexact = 0
+    for cfg in ("a", "b"):
+        m = Matcher()
+        m.window, m.threshcount, m.search_depth = (int(x) for x in gm["cfg_" + cfg])
+        keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+        batch = m.match_batch(ht, [gm[k + "/q"] for k in keys])
+        for key, rows in zip(keys, batch):
+            q = gm[key + "/q"]
+            if cfg == "a":
+                assert np.array_equal(ht.get_hits(q), gm["%s/%s/hits" % (db, key)])
+            want = gm["%s/%s/rows_%s" % (db, key, cfg)]
+            tie_w, tie_c = gm["%s/%s/ties_%s" % (db, key, cfg)]
+            # the oracle defines the tie order; the CUDA path must equal it always
+            orows = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=m.window,
+                                     threshcount=m.threshcount, search_depth=m.search_depth)
+            assert sorted(map(tuple, rows)) == sorted(map(tuple, orows)), (db, key, cfg)
+            if not tie_w and not tie_c:
+                assert np.array_equal(rows, want), (db, key, cfg)
+                assert np.array_equal(m.match_hashes(ht, q), want)
+                nexact += 1
+            else:
+                assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1])
+    assert nexact > 15
+
+
+def test_match_file_level_api(tmp_path):
+    """wavfile2hashes / ingest / match_file / file_match_to_msgs through WAV files."""
+    import wave
+    names = []
+    for i in range(4):
+        pcm = synth_track(700 + i, 12.0)
+        fn = str(tmp_path / ("t%d.wav" % i))
+        with wave.open(fn, "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(11025)
+            w.writeframes(pcm.tobytes())
+        names.append(fn)
+    an = Analyzer()
+    ht = HashTable()
+    for fn in names:
+        dur, nh = an.ingest(ht, fn)
+        assert abs(dur - 12.0) < 1e-6 and nh > 100
+    assert an.soundfilecount == 4 and abs(an.soundfiletotaldur - 48.0) < 1e-6
+    qpcm, off = synth_query(synth_track(702, 12.0), 42, seconds=6.0, noise_sigma=0.01)
+    qfn = str(tmp_path / "q.wav")
+    with wave.open(qfn, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(11025)
+        w.writeframes(qpcm.tobytes())
+    qan = Analyzer()
+    qan.shifts = 4
+    m = Matcher()
+    m.window = 2
+    rows, dur, nh = m.match_file(qan, ht, qfn)
+    assert rows.shape == (1, 7) and rows[0, 0] == 2 and abs(rows[0, 2] - off // 256) <= 1
+    msgs = m.file_match_to_msgs(qan, ht, qfn)
+    assert msgs == [qfn + "\t" + names[2]]
+    with pytest.raises(IOError):
+        an.wavfile2hashes(str(tmp_path / "missing.wav"))
+    an.fail_on_error = False
+    assert len(an.wavfile2hashes(str(tmp_path / "missing.wav"))) == 0
