@@ -41,6 +41,8 @@ _SIGS = {
     "afp_set_stream": (C.c_int, [_P, _P]),
     "afp_sync": (C.c_int, [_P]),
     "afp_launch_count": (C.c_int64, [_P]),
+    "afp_set_profiling": (C.c_int, [_P, C.c_int]),
+    "afp_get_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "afp_set_analyzer": (C.c_int, [_P, C.POINTER(AnalyzerParams), _P, _P, C.c_double]),
     "afp_fingerprint_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int32, _I64P, _I64P, _I64P]),
     "afp_fetch_hashes": (C.c_int, [_P, _P, C.c_int, _I64P]),
@@ -135,6 +137,14 @@ class Context:
 
     def sync(self):
         self.check(self.lib.afp_sync(self.h))
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.afp_set_profiling(self.h, 1 if on else 0))
+
+    def stage_ms(self):
+        out = (C.c_float * 5)()
+        self.check(self.lib.afp_get_stage_ms(self.h, out))
+        return [float(v) for v in out]
 
     def launch_count(self) -> int:
         return int(self.lib.afp_launch_count(self.h))

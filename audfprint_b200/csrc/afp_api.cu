@@ -50,6 +50,8 @@ void afp_destroy(afp_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i <= AFP_NSTAGES; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   DevBuf* bufs[] = {&c->d_window, &c->d_gauss, &c->d_twid, &c->d_pcm_stage, &c->d_items, &c->d_file_col_base,
                     &c->d_logs, &c->d_nyq, &c->d_tile_stats, &c->d_item_stats, &c->d_fwd_val, &c->d_fwd_bin,
                     &c->d_fwd_cnt, &c->d_pk_bin, &c->d_pk_cnt, &c->d_item_scols, &c->d_item_npeaks, &c->d_lm,
@@ -88,6 +90,24 @@ int afp_sync(afp_ctx* c) {
 }
 
 int64_t afp_launch_count(afp_ctx* c) { return c ? c->launches : -1; }
+
+int afp_set_profiling(afp_ctx* c, int enable) {
+  if (!c) return AFP_ERR_INVALID;
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  if (enable && !c->ev[0])
+    for (int i = 0; i <= AFP_NSTAGES; ++i) AFP_CUDA(c, cudaEventCreate(&c->ev[i]));
+  c->profiling = enable != 0;
+  c->ev_valid = false;
+  return AFP_OK;
+}
+
+int afp_get_stage_ms(afp_ctx* c, float* ms) {
+  if (!c || !ms) return AFP_ERR_INVALID;
+  if (!c->ev_valid) AFP_FAIL(c, AFP_ERR_STATE, "no profiled batch");
+  AFP_CUDA(c, cudaEventSynchronize(c->ev[AFP_NSTAGES]));
+  for (int i = 0; i < AFP_NSTAGES; ++i) AFP_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  return AFP_OK;
+}
 
 int afp_set_analyzer(afp_ctx* c, const afp_analyzer_params* p, const double* window, const double* gauss,
                      double f_sd) {
@@ -208,14 +228,24 @@ int afp_fingerprint_batch(afp_ctx* c, const void* pcm, int pcm_dtype, int pcm_on
   if (!c->analyzer_set) AFP_FAIL(c, AFP_ERR_STATE, "afp_set_analyzer has not been called");
   AFP_CUDA(c, cudaSetDevice(c->device));
   const void* dpcm = nullptr;
+#define AFP_MARK(i) do { if (c->profiling) AFP_CUDA(c, cudaEventRecord(c->ev[i], c->stream)); } while (0)
+  c->ev_valid = false;
+  AFP_MARK(0);
   int rc = prepare_batch(c, pcm, pcm_dtype, pcm_on_host, nfiles, sample_offsets, sample_lengths, c->ap.shifts, &dpcm);
   if (rc) return rc;
   c->total_hashes = -1;
+  AFP_MARK(1);
   if ((rc = afp_launch_stft(c, dpcm, pcm_dtype, nullptr))) return rc;
+  AFP_MARK(2);
   if ((rc = afp_launch_stats(c))) return rc;
+  AFP_MARK(3);
   if ((rc = afp_launch_peaks(c))) return rc;
+  AFP_MARK(4);
   if ((rc = afp_launch_hashes(c))) return rc;
   if ((rc = afp_write_hashes(c))) return rc;
+  AFP_MARK(5);
+  c->ev_valid = c->profiling;
+#undef AFP_MARK
   c->batch_valid = true;
   if (total_hashes) {
     AFP_CUDA(c, cudaMemcpyAsync(&c->total_hashes, c->d_file_off.as<int64_t>() + nfiles, sizeof(int64_t),

@@ -65,6 +65,9 @@ struct afp_ctx {
   bool own_stream = false;
   std::string err;
   int64_t launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[AFP_NSTAGES + 1] = {};
+  bool ev_valid = false;
 
   // analyzer configuration
   afp_analyzer_params ap{};

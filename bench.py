@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds fingerprinted per second (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
+                                                           # reference path on all host cores
+
+A "step" = one pass of the fingerprint hot path (K1 STFT/log -> K2 peaks -> K3
+hashes) over one batch of synthetic 11025 Hz mono int16 PCM.  At N=1 the batch
+is BASELINE.json configs[1]: 1024 x 30 s files (density 20, fanout 3, 5
+peaks/frame, 1 shift).  With N GPUs every rank fingerprints its own 1024 files
+(file sharding, no data-path collective): weak scaling.
+
+Prints ONE JSON line (rank 0).  `value` has the PCM already resident in HBM;
+`e2e` goes through Analyzer.fingerprint_packed with pinned HOST buffers, the
+host->device copy of the PCM and the device->host read of the hashes inside the
+timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 11025
+METRIC = "audio_seconds_fingerprinted_per_sec"
+UNIT = "audio-s/s"
+
+
+# ---------------------------------------------------------------- synthetic input
+def _gen(args):
+    seed, secs = args
+    from audfprint_b200.synth import synth_track
+    return synth_track(seed, secs)
+
+
+def make_tracks(pool, first_seed, nfiles, secs):
+    return pool.map(_gen, [(first_seed + i, secs) for i in range(nfiles)], chunksize=8)
+
+
+# ---------------------------------------------------------------- CPU arm (oracle)
+_TRACKS = None      # set before the CPU pool is forked: workers inherit the PCM, tasks are indices
+
+
+def _worker_init():
+    # pay the (cold-container) import cost before anything is timed
+    import scipy.signal  # noqa: F401
+    from oracle import afp_oracle  # noqa: F401
+    from audfprint_b200 import synth  # noqa: F401
+
+
+def _cpu_fp(i):
+    from oracle import afp_oracle as orc
+    from audfprint_b200.synth import pcm_to_float
+    return orc.fingerprint(pcm_to_float(_TRACKS[i]), density=20.0, fanout=3, shifts=1)
+
+
+def cpu_pool(tracks, nproc):
+    """Fork a pool whose workers already hold `tracks` (no per-task pickling of PCM)."""
+    global _TRACKS
+    _TRACKS = tracks
+    pool = mp.get_context("fork").Pool(nproc, initializer=_worker_init)
+    pool.map(_cpu_fp, range(min(len(tracks), nproc)), chunksize=1)      # warm every worker
+    return pool
+
+
+def cpu_pass(pool, n):
+    """Oracle port of the reference path over files 0..n-1 on the pool's processes
+    (file-level parallelism, as audfprint.py:249-265 does with joblib)."""
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_fp, range(n), chunksize=max(1, n // (8 * pool._processes)))
+    return time.perf_counter() - t0, out
+
+
+# ---------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--files", type=int, default=1024, help="files per GPU per step")
+    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--cpu-sample", type=int, default=512, help="files in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    nsamp = int(round(a.seconds * SR))
+    config = {"workload": "batch fingerprint %d x %g s synthetic 11025 Hz mono int16 files per GPU "
+                          "(BASELINE configs[1])" % (a.files, a.seconds),
+              "files_per_gpu": a.files, "seconds_per_file": a.seconds, "sr": SR, "density": 20, "fanout": 3,
+              "pks_per_frame": 5, "shifts": 1,
+              "cache": "inputs larger than L2 (%.0f MB int16 PCM + %.1f GB FP64 log-spectrogram per step)"
+                       % (a.files * nsamp * 2 / 1e6, a.files * (1 + nsamp // 256) * 2048 / 1e9),
+              "parallelism": "file-sharded x%d, no collective" % world}
+
+    # worker pools are forked BEFORE torch/CUDA is touched
+    pool = mp.get_context("fork").Pool(cores, initializer=_worker_init)
+
+    # ------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        per_step = min(max(cores * 4, 32), a.files)
+        tracks = make_tracks(pool, 0, per_step, a.seconds)
+        pool.close()
+        cpool = cpu_pool(tracks, cores)
+        for _ in range(min(a.warmup, 1)):
+            cpu_pass(cpool, per_step)
+        times = []
+        for _ in range(a.steps):
+            dt, _ = cpu_pass(cpool, per_step)
+            times.append(dt)
+        tot = sum(times)
+        val = per_step * a.seconds * a.steps / tot
+        sample = "%d of the %d files per step, oracle port (NumPy/SciPy, same call structure as the " \
+                 "reference) over a %d-process pool" % (per_step, a.files, cores)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                           "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------ our arm
+    tracks = make_tracks(pool, rank * a.files, a.files, a.seconds)
+    pool.close()
+    want_cpu = rank == 0 and world == 1 and not a.no_cpu_baseline
+    cpool = cpu_pool(tracks[:min(a.cpu_sample, a.files)], cores) if want_cpu else None
+
+    import torch
+    import torch.distributed as dist
+    from audfprint_b200 import Analyzer, _lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # pack: every file starts on a 16-byte boundary (TMA staging of interior tiles)
+    stride = (nsamp + 7) // 8 * 8
+    host_pcm = torch.zeros(a.files * stride + 8, dtype=torch.int16).pin_memory()
+    hp = host_pcm.numpy()
+    for i, t in enumerate(tracks):
+        hp[i * stride:i * stride + nsamp] = t
+    offs = np.arange(a.files + 1, dtype=np.int64) * stride
+    lens = np.full(a.files, nsamp, np.int64)
+    dev_pcm = host_pcm.cuda(non_blocking=False)
+    audio_s = a.files * a.seconds
+
+    an = Analyzer(device=local_rank)
+    ctx = _lib.context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)        # kernels + our timing events on the same stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        an.fingerprint_packed(dev_pcm, offs, fetch=False, sample_lengths=lens)
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) + live per-stage timing (roofline) ----------------
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stages = np.zeros(5)
+    e0.record(stream)
+    for _ in range(a.steps):
+        step_resident()
+        stages += np.array(ctx.stage_ms())
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    ctx.set_profiling(False)
+    stages /= a.steps
+
+    # ---- end to end: pinned host PCM in, hashes + offsets out, every step --------------------
+    rows, roff = an.fingerprint_packed(dev_pcm, offs, sample_lengths=lens)
+    nhash = int(roff[-1])
+    host_rows = torch.empty((nhash + 1024, 2), dtype=torch.int32).pin_memory()
+    hr = host_rows.numpy()
+    for _ in range(2):
+        an.fingerprint_packed(hp, offs, sample_lengths=lens, host_rows=hr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r2, o2 = an.fingerprint_packed(hp, offs, sample_lengths=lens, host_rows=hr)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert int(o2[-1]) == nhash and np.array_equal(r2, rows)
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- CPU baseline on a bounded sample + parity spot check (rank 0, N=1 only) -------------
+    cpu = None
+    parity = None
+    if want_cpu:
+        ns = min(a.cpu_sample, a.files)
+        dt, want = cpu_pass(cpool, ns)
+        bad = sum(0 if np.array_equal(rows[roff[i]:roff[i + 1]], want[i]) else 1 for i in range(ns))
+        parity = {"files_checked": ns, "files_mismatched": bad,
+                  "hashes_checked": int(sum(len(w) for w in want))}
+        cpu = {"value": ns * a.seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the %d files (%.0f audio-s), oracle port on a %d-process pool, %.1f s wall"
+                         % (ns, a.files, ns * a.seconds, cores, dt)}
+
+    if rank == 0:
+        peak, which = measured_peaks()
+        T = 1 + nsamp // 256
+        k1_bytes = a.files * (2 * nsamp + 8 * 256 * T + 8 * T)      # int16 PCM in, FP64 logs + nyq out
+        k1_ms = float(stages[1])
+        achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        out = {"metric": METRIC, "value": audio_s * world * a.steps / (ms_total * 1e-3), "unit": UNIT,
+               "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": config, "clocks": clocks,
+               "e2e": {"value": audio_s * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(hp.nbytes + offs.nbytes + lens.nbytes),
+                       "d2h_bytes_per_step": int(nhash * 8 + roff.nbytes + 8),
+                       "ms_per_step": e2e_ms / a.steps},
+               "gpu_launches": int(launches),
+               "roofline": {"kernel": "afp_stft_kernel<int16> (K1: frame+window+512-pt real FFT+log|.|, FP64)",
+                            "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": k1_ms},
+               "stages_ms": {"h2d": float(stages[0]), "k1_stft_log": float(stages[1]),
+                             "stats": float(stages[2]), "k2_peaks": float(stages[3]),
+                             "k3_hashes": float(stages[4])},
+               "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    if cpool:
+        cpool.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

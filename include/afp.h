@@ -84,6 +84,14 @@ int afp_sync(afp_ctx* ctx);
 /* Number of kernel launches issued by this context so far (bench accounting). */
 int64_t afp_launch_count(afp_ctx* ctx);
 
+/* Stage timing of afp_fingerprint_batch with CUDA events on the context's stream
+ * (bench.py's live roofline measurement).  Stages: 0 host->device PCM copy,
+ * 1 K1 stft+log, 2 per-item statistics, 3 K2 peaks, 4 K3 landmarks/merge/write.
+ * afp_get_stage_ms synchronises and returns the last batch's durations. */
+#define AFP_NSTAGES 5
+int afp_set_profiling(afp_ctx* ctx, int enable);
+int afp_get_stage_ms(afp_ctx* ctx, float* ms /* [AFP_NSTAGES] */);
+
 /* ---- Analyzer --------------------------------------------------------------
  * Replaces stft.stft (stft.py:62-94) + Analyzer.find_peaks
  * (audfprint_analyze.py:255-308) + peaks2landmarks (:310-343) +

@@ -65,10 +65,18 @@ def stft_complex(d: np.ndarray, n_fft: int = N_FFT, n_hop: int = N_HOP) -> np.nd
     return np.fft.rfft(frames, n_fft).transpose()                  # stft.py:94
 
 
-def hpf_rows(x: np.ndarray, pole: float = HPF_POLE) -> np.ndarray:
+def hpf_rows(x: np.ndarray, pole: float = HPF_POLE, explicit: bool = False) -> np.ndarray:
     """Per-row lfilter([1,-1],[1,-pole]) with zero initial state, in
     scipy's direct-form-II-transposed order: y = z + x ; z = -x + pole*y.
-    audfprint_analyze.py:293-295."""
+    audfprint_analyze.py:293-295.  When scipy is importable the same C routine
+    the reference calls is used (one call over all rows); the explicit
+    recurrence below is bit-identical to it (tests/test_oracle_golden.py)."""
+    if not explicit:
+        try:
+            import scipy.signal
+            return scipy.signal.lfilter([1, -1], [1, -pole], x, axis=1)
+        except ImportError:
+            pass
     rows, cols = x.shape
     y = np.empty_like(x)
     z = np.zeros(rows, dtype=x.dtype)
