@@ -3,6 +3,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 
 #include "afp_internal.cuh"
@@ -28,14 +29,24 @@ int afp_create(afp_ctx** out, int device) {
     return AFP_ERR_CUDA;
   }
   c->own_stream = true;
-  // FFT twiddles: W256^k (k < 256) then W512^k (k < 256), as (cos, -sin)
-  std::vector<double> tw(2 * 512);
-  const double pi = 3.14159265358979323846;
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  // double2 tables: tw256[p][r] = W256^(r p); W512^k (k < 256); log table (c_i, -0.5 log c_i)
+  std::vector<double> tw(2 * (256 + 256 + 128));
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int p = 0; p < 16; ++p)
+    for (int r = 0; r < 16; ++r) {
+      const int e = (r * p) & 255;
+      tw[2 * (p * 16 + r)] = (double)cosl(2.0L * pi * e / 256.0L);
+      tw[2 * (p * 16 + r) + 1] = (double)(-sinl(2.0L * pi * e / 256.0L));
+    }
   for (int k = 0; k < 256; ++k) {
-    tw[2 * k] = cos(2.0 * pi * k / 256.0);
-    tw[2 * k + 1] = -sin(2.0 * pi * k / 256.0);
-    tw[512 + 2 * k] = cos(2.0 * pi * k / 512.0);
-    tw[512 + 2 * k + 1] = -sin(2.0 * pi * k / 512.0);
+    tw[512 + 2 * k] = (double)cosl(2.0L * pi * k / 512.0L);
+    tw[512 + 2 * k + 1] = (double)(-sinl(2.0L * pi * k / 512.0L));
+  }
+  for (int i = 0; i < 128; ++i) {
+    const double ci = (double)(1.0L / (1.0L + (i + 0.5L) / 128.0L));
+    tw[1024 + 2 * i] = ci;
+    tw[1024 + 2 * i + 1] = (double)(-0.5L * logl((long double)ci));
   }
   if (c->d_twid.reserve(tw.size() * sizeof(double)) != cudaSuccess ||
       cudaMemcpy(c->d_twid.p, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -52,7 +63,7 @@ void afp_destroy(afp_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i <= AFP_NSTAGES; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  DevBuf* bufs[] = {&c->d_window, &c->d_gauss, &c->d_twid, &c->d_pcm_stage, &c->d_items, &c->d_file_col_base,
+  DevBuf* bufs[] = {&c->d_window, &c->d_gauss, &c->d_twid, &c->d_pcm_stage, &c->d_items, &c->d_tile_item, &c->d_file_col_base,
                     &c->d_logs, &c->d_nyq, &c->d_tile_stats, &c->d_item_stats, &c->d_fwd_val, &c->d_fwd_bin,
                     &c->d_fwd_cnt, &c->d_pk_bin, &c->d_pk_cnt, &c->d_item_scols, &c->d_item_npeaks, &c->d_lm,
                     &c->d_col_cnt, &c->d_file_tot, &c->d_file_off, &c->d_hashes, &c->d_pk_off, &c->d_pk_rows,
@@ -60,6 +71,15 @@ void afp_destroy(afp_ctx* c) {
                     &c->d_hit_off, &c->d_hits, &c->d_mscratch, &c->d_mcounters, &c->d_mrows, &c->d_mrow_cnt,
                     &c->d_mrow_off, &c->d_mrows_packed};
   for (DevBuf* b : bufs) b->release();
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->ev_batch_done) cudaEventDestroy(c->ev_batch_done);
+    for (int i = 0; i < 4; ++i) {
+      if (c->chunk_stream[i]) cudaStreamDestroy(c->chunk_stream[i]);
+      if (c->ev_chunk_stream[i]) cudaEventDestroy(c->ev_chunk_stream[i]);
+    }
+  }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -121,10 +141,12 @@ int afp_set_analyzer(afp_ctx* c, const afp_analyzer_params* p, const double* win
   if (p->mindt < 0 || p->targetdt <= p->mindt || p->targetdt > 64 || p->targetdf < 1 || p->targetdf > 32)
     AFP_FAIL(c, AFP_ERR_INVALID, "pairing window outside the 6-bit hash fields");
   if (!(p->a_dec > 0.0) || !(f_sd > 0.0 || gauss)) AFP_FAIL(c, AFP_ERR_INVALID, "bad a_dec / f_sd");
-  std::vector<double> w(AFP_N_FFT), g(AFP_GAUSS_N);
+  std::vector<double> w(2 * AFP_N_FFT), g(AFP_GAUSS_N);
   const double pi = 3.14159265358979323846;
-  for (int k = 0; k < AFP_N_FFT; ++k)   // np.hanning(514)[1:-1]
+  for (int k = 0; k < AFP_N_FFT; ++k) {   // np.hanning(514)[1:-1]
     w[k] = window ? window[k] : 0.5 - 0.5 * cos(2.0 * pi * (k + 1) / (AFP_N_FFT + 1));
+    w[AFP_N_FFT + k] = w[k] * (1.0 / 32768.0);   // exact: (x/32768)*w == x*(w/32768)
+  }
   for (int j = 0; j < AFP_GAUSS_N; ++j) {
     const double u = (double)(j - AFP_NBINS) / f_sd;
     g[j] = gauss ? gauss[j] : exp(-0.5 * (u * u));
@@ -144,7 +166,8 @@ int afp_set_analyzer(afp_ctx* c, const afp_analyzer_params* p, const double* win
 
 // Build the item table of a batch, size the workspace, stage the PCM.
 static int prepare_batch(afp_ctx* c, const void* pcm, int dtype, int on_host, int32_t nfiles,
-                         const int64_t* off, const int64_t* lens, int shifts, const void** pcm_dev) {
+                         const int64_t* off, const int64_t* lens, int shifts, const void** pcm_dev,
+                         bool chunked = false) {
   if (dtype != AFP_PCM_I16 && dtype != AFP_PCM_F32) AFP_FAIL(c, AFP_ERR_INVALID, "unknown pcm dtype");
   if (nfiles < 0 || (nfiles > 0 && (!off || !pcm))) AFP_FAIL(c, AFP_ERR_INVALID, "null pcm / offsets");
   for (int f = 0; f < nfiles; ++f) {
@@ -185,6 +208,7 @@ static int prepare_batch(afp_ctx* c, const void* pcm, int dtype, int on_host, in
   const size_t fr = (size_t)frames + 1;
   AFP_CUDA(c, c->d_items.reserve(sizeof(ItemDesc) * (size_t)(c->nitems + 1)));
   AFP_CUDA(c, c->d_file_col_base.reserve(sizeof(int64_t) * (size_t)(nfiles + 1)));
+  AFP_CUDA(c, c->d_tile_item.reserve(sizeof(int32_t) * (size_t)(tiles + 1)));
   AFP_CUDA(c, c->d_logs.reserve(sizeof(double) * AFP_NBINS * fr));
   AFP_CUDA(c, c->d_nyq.reserve(sizeof(double) * fr));
   AFP_CUDA(c, c->d_tile_stats.reserve(sizeof(double) * 3 * (size_t)(tiles + 1)));
@@ -212,12 +236,81 @@ static int prepare_batch(afp_ctx* c, const void* pcm, int dtype, int on_host, in
     const size_t esz = dtype == AFP_PCM_I16 ? 2 : 4;
     const size_t bytes = (size_t)(off[nfiles] - off[0]) * esz;
     AFP_CUDA(c, c->d_pcm_stage.reserve(bytes + 16));
-    AFP_CUDA(c, cudaMemcpyAsync(c->d_pcm_stage.p, (const char*)pcm + (size_t)off[0] * esz, bytes,
-                                cudaMemcpyHostToDevice, c->stream));
     // staged copy starts at sample off[0]: rebase the pointer so that item offsets still apply
     *pcm_dev = (const char*)c->d_pcm_stage.p - (size_t)off[0] * esz;
+    if (!chunked)
+      AFP_CUDA(c, cudaMemcpyAsync(c->d_pcm_stage.p, (const char*)pcm + (size_t)off[0] * esz, bytes,
+                                  cudaMemcpyHostToDevice, c->stream));
   }
   return AFP_OK;
+}
+
+// Host-resident PCM: copy the batch in file chunks on a second stream and start
+// the kernels of a chunk as soon as its samples have landed, so that the PCIe
+// transfer (the end-to-end bound: 22 KB per audio-second) overlaps the compute.
+static int run_chunked(afp_ctx* c, const void* pcm, int dtype, int32_t nfiles, const int64_t* off,
+                       const void* dpcm) {
+  const size_t esz = dtype == AFP_PCM_I16 ? 2 : 4;
+  const int S = c->ap.shifts;
+  if (!c->copy_stream) {
+    AFP_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_chunk) AFP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch_done, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) {
+      AFP_CUDA(c, cudaStreamCreateWithFlags(&c->chunk_stream[i], cudaStreamNonBlocking));
+      AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_chunk_stream[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t total = (size_t)(off[nfiles] - off[0]) * esz;
+  // K2's duration is set by the file length, not by the number of files, so chunks are
+  // few and their kernel chains run on 4 streams so that the K2s of different chunks overlap
+  int nch = (int)std::min<size_t>(8, std::max<size_t>(1, total / ((size_t)40 << 20)));
+  nch = std::min(nch, nfiles);
+  // the staging buffer may still be read by the previous batch's kernels
+  AFP_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
+  AFP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
+  for (int i = 0; i < 4; ++i) AFP_CUDA(c, cudaStreamWaitEvent(c->chunk_stream[i], c->ev_batch_done, 0));
+  std::vector<int> fb(nch + 1, 0);
+  int f = 0;
+  for (int k = 0; k < nch; ++k) {
+    fb[k] = f;
+    const size_t target = (size_t)off[0] * esz + total * (size_t)(k + 1) / (size_t)nch;
+    while (f < nfiles && ((size_t)off[f + 1] * esz <= target || f == fb[k])) ++f;
+    if (k == nch - 1) f = nfiles;
+    const size_t b0 = (size_t)off[fb[k]] * esz, b1 = (size_t)off[f] * esz;
+    if (b1 > b0)
+      AFP_CUDA(c, cudaMemcpyAsync((char*)c->d_pcm_stage.p + (b0 - (size_t)off[0] * esz), (const char*)pcm + b0,
+                                  b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
+    AFP_CUDA(c, cudaEventRecord(c->ev_chunk[k], c->copy_stream));
+  }
+  fb[nch] = nfiles;
+  int rc;
+  if ((rc = afp_launch_tile_table(c))) return rc;
+  AFP_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));   // item + tile tables are in place
+  for (int i = 0; i < 4; ++i) AFP_CUDA(c, cudaStreamWaitEvent(c->chunk_stream[i], c->ev_batch_done, 0));
+  cudaStream_t user = c->stream;
+  for (int k = 0; k < nch; ++k) {
+    const int f0 = fb[k], f1 = fb[k + 1];
+    if (f1 <= f0) continue;
+    c->stream = c->chunk_stream[k & 3];          // launchers issue on c->stream
+    cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0);
+    const int i0 = f0 * S, i1 = f1 * S;
+    const int64_t t0 = c->h_items[i0].tile_base;
+    const int64_t t1 = (i1 < c->nitems) ? c->h_items[i1].tile_base : c->total_tiles;
+    rc = (e == cudaSuccess) ? AFP_OK : AFP_ERR_CUDA;
+    if (!rc) rc = afp_launch_stft(c, dpcm, dtype, nullptr, t0, t1 - t0);
+    if (!rc) rc = afp_launch_stats(c, i0, i1 - i0);
+    if (!rc) rc = afp_launch_peaks(c, i0, i1 - i0);
+    if (!rc) rc = afp_launch_landmarks(c, i0, i1 - i0);
+    c->stream = user;
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 4; ++i) {
+    AFP_CUDA(c, cudaEventRecord(c->ev_chunk_stream[i], c->chunk_stream[i]));
+    AFP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chunk_stream[i], 0));
+  }
+  if ((rc = afp_launch_hashes(c))) return rc;
+  return afp_write_hashes(c);
 }
 
 extern "C" {
@@ -230,21 +323,30 @@ int afp_fingerprint_batch(afp_ctx* c, const void* pcm, int pcm_dtype, int pcm_on
   const void* dpcm = nullptr;
 #define AFP_MARK(i) do { if (c->profiling) AFP_CUDA(c, cudaEventRecord(c->ev[i], c->stream)); } while (0)
   c->ev_valid = false;
+  const bool chunked = pcm_on_host && nfiles > 1 && !c->profiling &&
+                       (sample_offsets[nfiles] - sample_offsets[0]) * (pcm_dtype == AFP_PCM_I16 ? 2 : 4) >= (64 << 20);
   AFP_MARK(0);
-  int rc = prepare_batch(c, pcm, pcm_dtype, pcm_on_host, nfiles, sample_offsets, sample_lengths, c->ap.shifts, &dpcm);
+  int rc = prepare_batch(c, pcm, pcm_dtype, pcm_on_host, nfiles, sample_offsets, sample_lengths, c->ap.shifts, &dpcm,
+                         chunked);
   if (rc) return rc;
   c->total_hashes = -1;
-  AFP_MARK(1);
-  if ((rc = afp_launch_stft(c, dpcm, pcm_dtype, nullptr))) return rc;
-  AFP_MARK(2);
-  if ((rc = afp_launch_stats(c))) return rc;
-  AFP_MARK(3);
-  if ((rc = afp_launch_peaks(c))) return rc;
-  AFP_MARK(4);
-  if ((rc = afp_launch_hashes(c))) return rc;
-  if ((rc = afp_write_hashes(c))) return rc;
-  AFP_MARK(5);
-  c->ev_valid = c->profiling;
+  if (chunked) {
+    if ((rc = run_chunked(c, pcm, pcm_dtype, nfiles, sample_offsets, dpcm))) return rc;
+  } else {
+    AFP_MARK(1);
+    if ((rc = afp_launch_tile_table(c))) return rc;
+    if ((rc = afp_launch_stft(c, dpcm, pcm_dtype, nullptr, 0, c->total_tiles))) return rc;
+    AFP_MARK(2);
+    if ((rc = afp_launch_stats(c, 0, c->nitems))) return rc;
+    AFP_MARK(3);
+    if ((rc = afp_launch_peaks(c, 0, c->nitems))) return rc;
+    AFP_MARK(4);
+    if ((rc = afp_launch_landmarks(c, 0, c->nitems))) return rc;
+    if ((rc = afp_launch_hashes(c))) return rc;
+    if ((rc = afp_write_hashes(c))) return rc;
+    AFP_MARK(5);
+    c->ev_valid = c->profiling;
+  }
 #undef AFP_MARK
   c->batch_valid = true;
   if (total_hashes) {
@@ -330,9 +432,10 @@ static int single_signal(afp_ctx* c, const void* pcm, int dtype, int on_host, in
     AFP_CUDA(c, c->d_tmp.reserve(sizeof(double) * width * T));
     dout = c->d_tmp.as<double>();
   }
-  if ((rc = afp_launch_stft(c, dpcm, dtype, want_mag ? dout : nullptr))) return rc;
+  if ((rc = afp_launch_tile_table(c))) return rc;
+  if ((rc = afp_launch_stft(c, dpcm, dtype, want_mag ? dout : nullptr, 0, c->total_tiles))) return rc;
   if (!want_mag) {
-    if ((rc = afp_launch_stats(c))) return rc;
+    if ((rc = afp_launch_stats(c, 0, c->nitems))) return rc;
     if ((rc = afp_launch_sgram(c, dout))) return rc;
   }
   if (out_on_host)

@@ -17,6 +17,7 @@ namespace {
 
 struct HashArgs {
   const ItemDesc* items;
+  int item0;
   int nitems, nfiles, shifts, maxpks, fanout, targetdf, mindt, targetdt;
   const uint8_t* pk_bin;
   const uint8_t* pk_cnt;
@@ -32,8 +33,8 @@ struct HashArgs {
 
 // One CTA per item; each thread owns (column, slot) source peaks.
 __global__ void __launch_bounds__(256) afp_landmark_kernel(HashArgs a) {
-  const ItemDesc it = a.items[blockIdx.x];
-  const int scols = a.item_scols[blockIdx.x];   // last peak column + 1 (:321)
+  const ItemDesc it = a.items[a.item0 + blockIdx.x];
+  const int scols = a.item_scols[a.item0 + blockIdx.x];   // last peak column + 1 (:321)
   const int T = it.nframes, P = a.maxpks, F = a.fanout;
   const int64_t base = it.frame_base;
   for (int e = threadIdx.x; e < T * P; e += blockDim.x) {
@@ -206,6 +207,7 @@ __global__ void afp_lm_rows_kernel(const uint32_t* lm, int T, int PF, int32_t* c
 static HashArgs make_args(afp_ctx* c) {
   HashArgs a;
   a.items = c->d_items.as<ItemDesc>();
+  a.item0 = 0;
   a.nitems = c->nitems;
   a.nfiles = c->nfiles;
   a.shifts = c->ap.shifts;
@@ -301,14 +303,19 @@ int afp_launch_scan_i32_to_i64(afp_ctx* c, const int32_t* in, int64_t* out, int6
   return AFP_OK;
 }
 
+int afp_launch_landmarks(afp_ctx* c, int item0, int nitems) {
+  if (nitems <= 0 || c->total_frames == 0) return AFP_OK;
+  HashArgs a = make_args(c);
+  a.item0 = item0;
+  afp_landmark_kernel<<<nitems, 256, 0, c->stream>>>(a);
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches++;
+  return AFP_OK;
+}
+
 int afp_launch_hashes(afp_ctx* c) {
   if (c->nfiles == 0) return AFP_OK;
   HashArgs a = make_args(c);
-  if (c->nitems > 0 && c->total_frames > 0) {
-    afp_landmark_kernel<<<c->nitems, 256, 0, c->stream>>>(a);
-    AFP_CUDA(c, cudaGetLastError());
-    c->launches++;
-  }
   if (c->total_cols > 0) {
     afp_merge_kernel<false><<<(unsigned)((c->total_cols + 127) / 128), 128, 0, c->stream>>>(a);
     AFP_CUDA(c, cudaGetLastError());

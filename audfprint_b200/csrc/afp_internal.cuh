@@ -61,6 +61,7 @@ struct TableDev {
 
 struct afp_ctx {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -68,13 +69,19 @@ struct afp_ctx {
   bool profiling = false;
   cudaEvent_t ev[AFP_NSTAGES + 1] = {};
   bool ev_valid = false;
+  // host->device pipelining of afp_fingerprint_batch (pcm_on_host)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[32] = {};
+  cudaEvent_t ev_batch_done = nullptr;
+  cudaStream_t chunk_stream[4] = {};   // chunks are processed round-robin on these
+  cudaEvent_t ev_chunk_stream[4] = {};
 
   // analyzer configuration
   afp_analyzer_params ap{};
   bool analyzer_set = false;
-  DevBuf d_window;   // 512 doubles
+  DevBuf d_window;   // 2 x 512 doubles: window, then window * 2^-15 (int16 PCM)
   DevBuf d_gauss;    // AFP_GAUSS_N doubles
-  DevBuf d_twid;     // FFT twiddles: W256 (256 x double2) then W512 (257 x double2)
+  DevBuf d_twid;     // double2 tables: tw256[p][r] (256), W512^k (256), log table (128)
 
   // batch state (valid after afp_fingerprint_batch)
   int32_t nfiles = 0, nitems = 0;
@@ -86,6 +93,7 @@ struct afp_ctx {
 
   DevBuf d_pcm_stage;      // host->device staging when pcm_on_host
   DevBuf d_items;          // ItemDesc[nitems]
+  DevBuf d_tile_item;      // int32[total_tiles] item of every K1 tile
   DevBuf d_file_col_base;  // int64[nfiles+1]
   DevBuf d_logs;           // double [total_frames][256]   log|S|, bins 0..255
   DevBuf d_nyq;            // double [total_frames]        log|S| of the Nyquist bin
@@ -135,11 +143,14 @@ struct afp_ctx {
   } while (0)
 
 // ---- kernel launchers (defined in the .cu files) -------------------------------
-int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out /* optional [T][257] */);
-int afp_launch_stats(afp_ctx* c);
+int afp_launch_tile_table(afp_ctx* c);
+int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out /* optional [T][257] */, int64_t tile0,
+                    int64_t ntiles);
+int afp_launch_stats(afp_ctx* c, int item0, int nitems);
 int afp_launch_sgram(afp_ctx* c, double* sgram_out);
-int afp_launch_peaks(afp_ctx* c);
-int afp_launch_hashes(afp_ctx* c);
+int afp_launch_peaks(afp_ctx* c, int item0, int nitems);
+int afp_launch_landmarks(afp_ctx* c, int item0, int nitems);
+int afp_launch_hashes(afp_ctx* c);   // merge / scans (all files)
 int afp_write_hashes(afp_ctx* c);
 int afp_landmarks_from_peaks_impl(afp_ctx* c, const int32_t* rows, int64_t n, int on_host, int64_t* nlm);
 int afp_compact_peaks(afp_ctx* c, int shift);

@@ -26,7 +26,7 @@ constexpr unsigned FULL = 0xffffffffu;
 struct PeakArgs {
   const ItemDesc* items;
   const ItemStats* stats;
-  int nitems;
+  int item0;
   const double* logs;     // [frames][256]
   const double* gauss;    // AFP_GAUSS_N
   double a_dec, pole;
@@ -118,10 +118,12 @@ __device__ __forceinline__ void hpf_step(const double (&l)[8], double (&z)[8], d
   }
 }
 
+constexpr int PF = 4;   // prefetch distance (columns) of the forward / backward loops
+
 __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
   __shared__ double sE[AFP_GAUSS_PAD];
   const int lane = threadIdx.x;
-  const int item = blockIdx.x;
+  const int item = a.item0 + blockIdx.x;
   for (int k = lane; k < AFP_GAUSS_N; k += 32) sE[gidx(k)] = a.gauss[k];
   __syncwarp();
 
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
   const double lf = st.logfloor, mean = st.mean, pole = a.pole, a_dec = a.a_dec;
   ColLoader ld{reinterpret_cast<const double2*>(a.logs) + base * (AFP_NBINS / 2)};
 
-  double thr[8], z[8], s[8], l0[8], l1[8];
+  double thr[8], z[8], s[8], sn[8];
+  double lb[PF][8];   // register ring of prefetched columns (memory latency >> one column step)
 
   // ---- initial threshold: spread of the per-bin max over the first 10 columns
   // (audfprint_analyze.py:204-206)
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     for (int j = 0; j < 8; ++j) { z[j] = 0.0; mx[j] = -INFINITY; }
     const int n0 = min(10, T);
     for (int t = 0; t < n0; ++t) {
-      ld.load(t, lane, l0);
-      hpf_step(l0, z, s, lf, mean, pole);
+      ld.load(t, lane, lb[0]);
+      hpf_step(lb[0], z, s, lf, mean, pole);
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmax(mx[j], s[j]);
     }
@@ -161,50 +164,68 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
   }
 
   // ---- forward pass (audfprint_analyze.py:214-230) ------------------------------
+  // Software pipeline: column t+1 is high-passed and local-max'ed (independent of
+  // the threshold) before the threshold-dependent decisions of column t.
 #pragma unroll
   for (int j = 0; j < 8; ++j) z[j] = 0.0;
-  ld.load(0, lane, l0);
-  if (T > 1) ld.load(1, lane, l1);
-  for (int t = 0; t < T; ++t) {
-    hpf_step(l0, z, s, lf, mean, pole);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) l0[j] = l1[j];
-    if (t + 2 < T) ld.load(t + 2, lane, l1);
-
-    unsigned cmask = locmax_mask(s, lane);
+  for (int u = 0; u < PF; ++u)
+    if (u < T) ld.load(u, lane, lb[u]);
+  hpf_step(lb[0], z, s, lf, mean, pole);
+  unsigned lm = locmax_mask(s, lane);
+  if (PF < T) ld.load(PF, lane, lb[0]);
+  for (int t0 = 0; t0 < T; t0 += PF) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cmask &= (s[j] > thr[j]) ? ~0u : ~(1u << j);
-    int npk = 0;
-    if (__ballot_sync(FULL, cmask != 0)) {
-      // accept candidates by (value desc, bin desc) (:220), at most maxpks (:221)
-      while (true) {
-        unsigned long long bk = 0ull;
-        int bj = -1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const unsigned long long k = (unsigned long long)__double_as_longlong(s[j]);
-          if (((cmask >> j) & 1u) && k >= bk) { bk = k; bj = j; }
+    for (int u = 0; u < PF; ++u) {
+      const int t = t0 + u;
+      if (t < T) {   // warp-uniform
+        unsigned lmn = 0;
+        if (t + 1 < T) {
+          hpf_step(lb[(u + 1) % PF], z, sn, lf, mean, pole);
+          lmn = locmax_mask(sn, lane);
+          if (t + 1 + PF < T) ld.load(t + 1 + PF, lane, lb[(u + 1) % PF]);
         }
-        const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
-        const unsigned mhi = __reduce_max_sync(FULL, bj >= 0 ? hi : 0u);
-        const bool v1 = bj >= 0 && hi == mhi;
-        const unsigned mlo = __reduce_max_sync(FULL, v1 ? lo : 0u);
-        const bool v2 = v1 && lo == mlo;
-        const int pos = (int)__reduce_max_sync(FULL, v2 ? (unsigned)(8 * lane + bj + 1) : 0u) - 1;
-        const double val = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        if (lane == (pos >> 3)) cmask &= ~(1u << (pos & 7));
-        bump(thr, sE, lane, pos, val);
-        if (lane == 0) {
-          a.fwd_val[(base + t) * maxpks + npk] = val;
-          a.fwd_bin[(base + t) * maxpks + npk] = (uint8_t)pos;
+        unsigned cmask = lm;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cmask &= (s[j] > thr[j]) ? ~0u : ~(1u << j);
+        int npk = 0;
+        if (__ballot_sync(FULL, cmask != 0)) {
+          // accept candidates by (value desc, bin desc) (:220), at most maxpks (:221)
+          while (true) {
+            unsigned long long bk = 0ull;
+            int bj = -1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const unsigned long long k = (unsigned long long)__double_as_longlong(s[j]);
+              if (((cmask >> j) & 1u) && k >= bk) { bk = k; bj = j; }
+            }
+            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+            const unsigned mhi = __reduce_max_sync(FULL, bj >= 0 ? hi : 0u);
+            const bool v1 = bj >= 0 && hi == mhi;
+            const unsigned mlo = __reduce_max_sync(FULL, v1 ? lo : 0u);
+            const bool v2 = v1 && lo == mlo;
+            const int pos = (int)__reduce_max_sync(FULL, v2 ? (unsigned)(8 * lane + bj + 1) : 0u) - 1;
+            const double val = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+            if (lane == (pos >> 3)) cmask &= ~(1u << (pos & 7));
+            bump(thr, sE, lane, pos, val);
+            if (lane == 0) {
+              a.fwd_val[(base + t) * maxpks + npk] = val;
+              a.fwd_bin[(base + t) * maxpks + npk] = (uint8_t)pos;
+            }
+            ++npk;
+            if (npk >= maxpks || !__ballot_sync(FULL, cmask != 0)) break;
+          }
         }
-        ++npk;
-        if (npk >= maxpks || !__ballot_sync(FULL, cmask != 0)) break;
+        if (lane == 0) a.fwd_cnt[base + t] = (uint8_t)npk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(thr[j], a_dec);
+        if (t + 1 < T) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] = sn[j];
+          lm = lmn;
+        }
       }
     }
-    if (lane == 0) a.fwd_cnt[base + t] = (uint8_t)npk;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(thr[j], a_dec);
   }
   __syncwarp();   // make lane 0's fwd_* stores visible to the whole warp
 
@@ -229,29 +250,45 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     if (c) scols = max(scols, col + 1);
     npeaks += c;
   };
-  for (int t = T - 1; t >= 0; --t) {
-    const int n = a.fwd_cnt[base + t];
-    double my_val = 0.0;
-    int my_bin = -1, cur_alive = 0;
-    if (lane < n) {
-      my_val = a.fwd_val[(base + t) * maxpks + lane];
-      my_bin = a.fwd_bin[(base + t) * maxpks + lane];
-    }
-    for (int k = 0; k < n; ++k) {   // stored order is already (value desc, bin desc) (:241)
-      const double val = __shfl_sync(FULL, my_val, k);
-      const int pos = __shfl_sync(FULL, my_bin, k);
-      const bool ok = val >= pick(thr, pos & 7);
-      if ((__ballot_sync(FULL, ok) >> (pos >> 3)) & 1u) {   // :242, decided by the owning lane
-        bump(thr, sE, lane, pos, val);                     // :244-245
-        if (lane == k) cur_alive = 1;
-        if (nxt_alive && nxt_bin == pos) nxt_alive = 0;    // :247-248 same bin, following column
-      }                                                    // else :251 the peak is dropped
-    }
+  // prefetch ring over columns T-1, T-2, ...: count + this lane's slot (if lane < maxpks)
+  int pc[PF], pb[PF];
+  double pv[PF];
+  const bool slot = lane < maxpks;
+  auto fetch = [&](int t, int& c, double& v, int& b) {
+    c = a.fwd_cnt[base + t];
+    v = slot ? a.fwd_val[(base + t) * maxpks + lane] : 0.0;    // stale beyond the count, never used
+    b = slot ? (int)a.fwd_bin[(base + t) * maxpks + lane] : -1;
+  };
 #pragma unroll
-    for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(a_dec, thr[j]);
-    if (t + 1 < T) emit(t + 1, nxt_bin, nxt_alive);
-    nxt_bin = my_bin;
-    nxt_alive = cur_alive;
+  for (int u = 0; u < PF; ++u)
+    if (T - 1 - u >= 0) fetch(T - 1 - u, pc[u], pv[u], pb[u]);
+  for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int t = t0 - u;
+      if (t >= 0) {   // warp-uniform
+        const int n = pc[u];
+        const double my_val = pv[u];
+        const int my_bin = (lane < n) ? pb[u] : -1;
+        if (t - PF >= 0) fetch(t - PF, pc[u], pv[u], pb[u]);
+        int cur_alive = 0;
+        for (int k = 0; k < n; ++k) {   // stored order is already (value desc, bin desc) (:241)
+          const double val = __shfl_sync(FULL, my_val, k);
+          const int pos = __shfl_sync(FULL, my_bin, k);
+          const bool ok = val >= pick(thr, pos & 7);
+          if ((__ballot_sync(FULL, ok) >> (pos >> 3)) & 1u) {   // :242, decided by the owning lane
+            bump(thr, sE, lane, pos, val);                     // :244-245
+            if (lane == k) cur_alive = 1;
+            if (nxt_alive && nxt_bin == pos) nxt_alive = 0;    // :247-248 same bin, following column
+          }                                                    // else :251 the peak is dropped
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(a_dec, thr[j]);
+        if (t + 1 < T) emit(t + 1, nxt_bin, nxt_alive);
+        nxt_bin = my_bin;
+        nxt_alive = cur_alive;
+      }
+    }
   }
   emit(0, nxt_bin, nxt_alive);
   if (lane == 0) {
@@ -302,12 +339,12 @@ __global__ void afp_gather_npeaks_kernel(const int32_t* item_npeaks, int nfiles,
 
 }  // namespace
 
-int afp_launch_peaks(afp_ctx* c) {
-  if (c->nitems == 0) return AFP_OK;
+int afp_launch_peaks(afp_ctx* c, int item0, int nitems) {
+  if (nitems <= 0) return AFP_OK;
   PeakArgs a;
   a.items = c->d_items.as<ItemDesc>();
   a.stats = c->d_item_stats.as<ItemStats>();
-  a.nitems = c->nitems;
+  a.item0 = item0;
   a.logs = c->d_logs.as<double>();
   a.gauss = c->d_gauss.as<double>();
   a.a_dec = c->ap.a_dec;
@@ -320,7 +357,7 @@ int afp_launch_peaks(afp_ctx* c) {
   a.pk_cnt = c->d_pk_cnt.as<uint8_t>();
   a.item_scols = c->d_item_scols.as<int32_t>();
   a.item_npeaks = c->d_item_npeaks.as<int32_t>();
-  afp_peaks_kernel<<<c->nitems, 32, 0, c->stream>>>(a);
+  afp_peaks_kernel<<<nitems, 32, 0, c->stream>>>(a);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
   return AFP_OK;

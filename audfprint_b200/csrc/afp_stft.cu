@@ -7,17 +7,23 @@
 // per-tile partials here and finished in afp_stats_kernel; the per-bin high-pass
 // (:293-295) is a time recursion and lives in the peak kernel (afp_peaks.cu).
 //
-// Work decomposition: one CTA = one tile of 16 consecutive frames of one item
-// (file x shift); 16 threads cooperate on a frame (256-point complex FFT as
-// 16 x 16, one shared-memory transpose, partner exchange by warp shuffle).
-// The hop-strided PCM of a tile is ONE contiguous run of 17*256 samples, staged
-// into shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) when the
-// tile is interior and 16-byte aligned, by reflected scalar loads otherwise.
+// Work decomposition: a tile = 16 consecutive frames of one item (file x shift).
+// PERSISTENT CTAs (2 per SM) walk the tile list; the hop-strided PCM of a tile
+// is ONE contiguous run of 17*256 samples, staged into a double-buffered shared
+// memory ring by 1-D TMA bulk copies (cp.async.bulk + mbarrier) issued one tile
+// ahead, so the copy of tile i+1 overlaps the FFTs of tile i (edge tiles and
+// unaligned files take a reflected scalar-load path).  16 threads cooperate on
+// a frame: 256-point complex FFT as 16 x 16 with one padded shared-memory
+// transpose, then the real-FFT split done on (k, 256-k) PAIRS so that each
+// partner exchange (warp shuffle) and each W512 twiddle serves two bins.
 //
 // Why FP64: the peak decisions downstream compare these values bit-for-bit the
 // way the reference's float64 NumPy path does; an FP32 spectrogram flips a
-// decision roughly once per 10^5 frames.
+// decision roughly once per 10^5 frames (DESIGN.md "Precision").  The kernel is
+// therefore bound by the FP64 pipe (64 lanes/clk/SM), not by HBM; the log is a
+// table-driven FP64 routine (10 FP64 ops instead of libdevice's ~30).
 #include <math.h>
+#include <algorithm>
 #include "afp_fft.cuh"
 #include "afp_internal.cuh"
 
@@ -27,14 +33,18 @@ constexpr int FT = AFP_FRAMES_PER_TILE;   // 16 frames per tile
 constexpr int XS = 17;                    // padded row stride of the 16x16 exchange
 constexpr int XF = 16 * XS;               // 272 doubles per frame per component
 constexpr int K1_THREADS = 256;
+constexpr int LOGTAB = 128;               // log table entries (7 mantissa bits)
 
 struct StftArgs {
   const void* pcm;
   const ItemDesc* items;
+  const int32_t* tile_item;   // [ntiles] item of every tile (built by afp_tile_table_kernel)
   int nitems;
-  const double* window;   // 512
-  const double2* w256;    // 256: (cos, -sin)(2 pi k / 256)
+  int tile_begin, tile_end;   // tile range of this launch (a chunk of the batch)
+  const double* window;   // 512 (pre-scaled by 2^-15 for int16 PCM)
+  const double2* tw256;   // [p][r] = W256^(r*p), (cos, -sin)
   const double2* w512;    // 256: (cos, -sin)(2 pi k / 512)
+  const double2* logtab;  // 128: (c_i, -0.5*log(c_i))
   double* logs;           // [frames][256]
   double* nyq;            // [frames]
   double* tile_stats;     // [tiles][3]
@@ -55,198 +65,322 @@ __device__ __forceinline__ int64_t reflect_index(int64_t j, int64_t n) {
   return r < n ? r : period - r;
 }
 
-__device__ __forceinline__ float pcm_to_f32(int16_t v) { return static_cast<float>(v) * (1.0f / 32768.0f); }
-__device__ __forceinline__ float pcm_to_f32(float v) { return v; }
+// exact small-int -> double without the (slow) I2F.F64 path: (1.5*2^52 + x) - 1.5*2^52
+__device__ __forceinline__ double int_to_double(int x) {
+  return __hiloint2double(0x43380000 + (x >> 31), x) - 6755399441055744.0;
+}
 
-template <typename PcmT, bool WRITE_MAG>
-__global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_win = reinterpret_cast<double*>(smem_raw);                 // 512
-  double2* s_w256 = reinterpret_cast<double2*>(s_win + 512);           // 256
-  double2* s_w512 = s_w256 + 256;                                      // 256
-  double* s_xr = reinterpret_cast<double*>(s_w512 + 256);              // FT * XF
-  double* s_xi = s_xr + FT * XF;                                       // FT * XF
-  double* s_red = s_xi + FT * XF;                                      // 3 * 8
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_red + 24);
-  PcmT* s_pcm = reinterpret_cast<PcmT*>(s_bar + 2);                    // (FT+1)*256, 16 B aligned
+// 0.5*log(0.25*v) for v > 0 normal; table-driven, |abs error| ~ 1e-16 + 0.5 ulp.
+//   v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m*c_i - 1, |r| <= 2^-8
+//   0.5*log(v/4) = (e-2)*ln2/2 + t_i + 0.5*log1p(r),  t_i = -0.5*log(c_i)
+// Inputs that are 0 / denormal / inf / nan give a meaningless value here; the
+// caller detects them with is_special() and patches with half_log_quarter_slow().
+__device__ __noinline__ double half_log_quarter_slow(double v) { return 0.5 * log(0.25 * v); }
+__device__ __forceinline__ bool is_special(double v) {
+  return (unsigned)(__double2hiint(v) - 0x00100000) >= 0x7fe00000u;
+}
 
-  const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
+__device__ __forceinline__ double half_log_quarter(double v, const double2* s_logtab) {
+  const int hi = __double2hiint(v);
+  const int lo = __double2loint(v);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 ct = s_logtab[(hi >> 13) & (LOGTAB - 1)];
+  const double r = fma(m, ct.x, -1.0);
+  double p = -0.5 / 6.0;
+  p = fma(p, r, 0.5 / 5.0);
+  p = fma(p, r, -0.5 / 4.0);
+  p = fma(p, r, 0.5 / 3.0);
+  p = fma(p, r, -0.5 / 2.0);
+  p = fma(p, r, 0.5);
+  const double ed = int_to_double((hi >> 20) - 1025);
+  return fma(ed, 0.34657359027997264, ct.y) + p * r;   // ln2/2
+}
 
-  // tile -> item (last item whose tile_base <= tile)
-  int lo = 0, hi = a.nitems;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (a.items[mid].tile_base <= tile) lo = mid; else hi = mid;
+template <typename PcmT> struct PcmTraits;
+template <> struct PcmTraits<int16_t> {
+  static constexpr int NBUF = 2;
+  __device__ static __forceinline__ void load2(const int16_t* p, double& a, double& b) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    a = int_to_double((int)(short)(w & 0xffffu));
+    b = int_to_double((int)w >> 16);
   }
-  const ItemDesc it = a.items[lo];
+};
+template <> struct PcmTraits<float> {
+  static constexpr int NBUF = 1;   // 2 x 17 KB would not leave room for two CTAs per SM
+  __device__ static __forceinline__ void load2(const float* p, double& a, double& b) {
+    const float2 w = *reinterpret_cast<const float2*>(p);
+    a = (double)w.x;
+    b = (double)w.y;
+  }
+};
+
+struct TileInfo {
+  int64_t frame0;     // batch-wide index of the tile's first frame
+  int64_t src;        // absolute sample index of the run's first sample (sample_start + j0)
+  int64_t j0;         // the same relative to the item (may be < 0)
+  int64_t nsamples;   // samples of the item (reflection period)
+  int nft;            // frames of the tile that exist
+  bool tma;           // interior + 16-byte aligned -> bulk copy
+};
+
+template <typename PcmT>
+__device__ __forceinline__ TileInfo make_tile(const StftArgs& a, const ItemDesc& it, int tile) {
+  TileInfo ti;
   const int t0 = (tile - it.tile_base) * FT;
-  const int nft = min(FT, it.nframes - t0);
-  const int64_t n = it.nsamples;
-  const int64_t j0 = (int64_t)(t0 - 1) * AFP_N_HOP;                 // first sample of the tile (may be < 0)
-  const int nsamp = (nft + 1) * AFP_N_HOP;
-  const PcmT* src = reinterpret_cast<const PcmT*>(a.pcm) + it.sample_start;
+  ti.frame0 = it.frame_base + t0;
+  ti.nft = min(FT, it.nframes - t0);
+  ti.j0 = (int64_t)(t0 - 1) * AFP_N_HOP;   // first sample of the run (may be < 0)
+  ti.src = it.sample_start + ti.j0;
+  ti.nsamples = it.nsamples;
+  const bool interior = (ti.j0 >= 0) && (ti.j0 + (ti.nft + 1) * AFP_N_HOP <= it.nsamples);
+  ti.tma = interior && ((reinterpret_cast<uintptr_t>(reinterpret_cast<const PcmT*>(a.pcm) + ti.src) & 15) == 0);
+  return ti;
+}
 
-  // ---- stage the PCM run -----------------------------------------------------
-  const bool interior = (j0 >= 0) && (j0 + nsamp <= n);
-  const bool use_tma = interior && ((reinterpret_cast<uintptr_t>(src + j0) & 15) == 0);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (use_tma) {
-    if (tid == 0) {
+// Stage the PCM run of a tile: TMA bulk copy (one thread) or reflected loads (all).
+template <typename PcmT>
+__device__ __forceinline__ void stage_tile(const StftArgs& a, const TileInfo& ti, PcmT* dst,
+                                           unsigned long long* bar) {
+  const PcmT* pcm = reinterpret_cast<const PcmT*>(a.pcm);
+  const int nsamp = (ti.nft + 1) * AFP_N_HOP;
+  if (ti.tma) {
+    if (threadIdx.x == 0) {
       const uint32_t bytes = nsamp * sizeof(PcmT);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(bytes)
+      // order earlier generic-proxy accesses of this buffer before the async-proxy write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                    : "memory");
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(s_pcm)),
-          "l"(src + j0), "r"(bytes), "r"(smem_u32(s_bar))
+              smem_u32(dst)),
+          "l"(pcm + ti.src), "r"(bytes), "r"(smem_u32(bar))
           : "memory");
     }
   } else {
-    for (int i = tid; i < nsamp; i += K1_THREADS) s_pcm[i] = src[reflect_index(j0 + i, n)];
+    const PcmT* item0 = pcm + (ti.src - ti.j0);
+    for (int i = threadIdx.x; i < nsamp; i += K1_THREADS) dst[i] = item0[reflect_index(ti.j0 + i, ti.nsamples)];
   }
-  // constant tables (L2-resident) while the bulk copy is in flight
+}
+
+__device__ __forceinline__ void wait_bar(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <typename PcmT, bool WRITE_MAG>
+__global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
+  constexpr int NBUF = PcmTraits<PcmT>::NBUF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_win = reinterpret_cast<double*>(smem_raw);                 // 512
+  double2* s_tw256 = reinterpret_cast<double2*>(s_win + 512);          // 256, [p][r]
+  double2* s_w512 = s_tw256 + 256;                                     // 256
+  double2* s_logtab = s_w512 + 256;                                    // 128
+  double* s_xr = reinterpret_cast<double*>(s_logtab + LOGTAB);         // FT * XF
+  double* s_xi = s_xr + FT * XF;                                       // FT * XF
+  double* s_red = s_xi + FT * XF;                                      // 3 * 8
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_red + 24);   // 2
+  PcmT* s_pcm = reinterpret_cast<PcmT*>(s_bar + 2);                    // NBUF * (FT+1)*256, 16 B aligned
+  constexpr int PCM_BUF = (FT + 1) * AFP_N_HOP;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int i = tid; i < 512; i += K1_THREADS) s_win[i] = a.window[i];
   for (int i = tid; i < 256; i += K1_THREADS) {
-    s_w256[i] = a.w256[i];
+    s_tw256[i] = a.tw256[i];
     s_w512[i] = a.w512[i];
   }
-  if (use_tma) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(smem_u32(s_bar)), "r"(0u)
-          : "memory");
-    }
-  }
+  for (int i = tid; i < LOGTAB; i += K1_THREADS) s_logtab[i] = a.logtab[i];
   __syncthreads();
 
   const int g = tid >> 4;   // frame within the tile
   const int r = tid & 15;   // cooperating thread within the frame
-  const bool active = g < nft;
-  const int64_t frame = it.frame_base + t0 + g;
+  const int lane = tid & 31;
+  const int src_lane = (lane & 16) | ((16 - r) & 15);
+  uint32_t phases = 0u;   // bit b = parity to wait for on barrier b
 
-  double vmax = 0.0, vmin = INFINITY, vsum = 0.0;
-  double zr[16], zi[16];
-  if (active) {
-    // step A: z[16q + r] = (x[2n] w[2n], x[2n+1] w[2n+1]), n = 16q + r
-    const PcmT* fr = s_pcm + g * AFP_N_HOP;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int i0 = 2 * (16 * q + r);
-      const double2 w = *reinterpret_cast<const double2*>(s_win + i0);
-      zr[q] = (double)pcm_to_f32(fr[i0]) * w.x;
-      zi[q] = (double)pcm_to_f32(fr[i0 + 1]) * w.y;
+  int tile = a.tile_begin + blockIdx.x;
+  if (tile >= a.tile_end) return;
+  const int G = gridDim.x;
+  // Tile descriptors are fetched two tiles ahead so that their (dependent) global
+  // loads never sit on the critical path: item index at distance 3, ItemDesc at 2.
+  TileInfo cur = make_tile<PcmT>(a, a.items[a.tile_item[tile]], tile);
+  TileInfo nxt = cur;
+  if (tile + G < a.tile_end) nxt = make_tile<PcmT>(a, a.items[a.tile_item[tile + G]], tile + G);
+  int item_nn = (tile + 2 * G < a.tile_end) ? a.tile_item[tile + 2 * G] : 0;
+  stage_tile<PcmT>(a, cur, s_pcm, s_bar);
+  int buf = 0;
+
+  for (; tile < a.tile_end; tile += G) {
+    const int next = tile + G;
+    // prefetch the next tile into the other buffer (free since the end-of-iteration barrier)
+    if (NBUF == 2 && next < a.tile_end) stage_tile<PcmT>(a, nxt, s_pcm + (buf ^ 1) * PCM_BUF, s_bar + (buf ^ 1));
+    ItemDesc desc_nn = a.items[item_nn];                                   // consumed at the end of the iteration
+    const int item_n3 = (tile + 3 * G < a.tile_end) ? a.tile_item[tile + 3 * G] : 0;   // consumed next iteration
+    if (cur.tma) {
+      wait_bar(s_bar + buf, (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+    } else {
+      __syncthreads();   // scalar-staged run is visible
     }
-    afp_fft16(zr, zi);
-    double* xr = s_xr + g * XF;
-    double* xi = s_xi + g * XF;
+
+    const bool active = g < cur.nft;
+    const int64_t frame = cur.frame0 + g;
+    double vmax = 0.0, vmin = INFINITY, vsum = 0.0;
+    double zr[16], zi[16];
+    if (active) {
+      // step A: z[16q + r] = (x[2n] w[2n], x[2n+1] w[2n+1]), n = 16q + r
+      const PcmT* fr = s_pcm + buf * PCM_BUF + g * AFP_N_HOP;
 #pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      const double2 w = s_w256[(r * p) & 255];
-      xr[p * XS + r] = zr[p] * w.x - zi[p] * w.y;
-      xi[p * XS + r] = zr[p] * w.y + zi[p] * w.x;
-    }
-  }
-  __syncwarp();
-  if (active) {
-    // step B: thread p = r transforms column p: Z[p + 16 s]
-    const double* xr = s_xr + g * XF + r * XS;
-    const double* xi = s_xi + g * XF + r * XS;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      zr[q] = xr[q];
-      zi[q] = xi[q];
-    }
-    afp_fft16(zr, zi);
-  }
-  // real-FFT post-processing: partner Z[(256-k)&255] sits in lane (16-p)&15,
-  // register 15-s (p > 0) or (16-s)&15 (p == 0, own registers).
-  {
-    const int lane = tid & 31;
-    const int src_lane = (lane & 16) | ((16 - r) & 15);
-    double* out = a.logs + frame * AFP_NBINS;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-      double c = __shfl_sync(0xffffffffu, zr[15 - s], src_lane);
-      double d = __shfl_sync(0xffffffffu, zi[15 - s], src_lane);
-      if (r == 0) {
-        c = zr[(16 - s) & 15];
-        d = zi[(16 - s) & 15];
+      for (int q = 0; q < 16; ++q) {
+        const int i0 = 2 * (16 * q + r);
+        const double2 w = *reinterpret_cast<const double2*>(s_win + i0);
+        double x0, x1;
+        PcmTraits<PcmT>::load2(fr + i0, x0, x1);
+        zr[q] = x0 * w.x;
+        zi[q] = x1 * w.y;
       }
-      if (active) {
-        const int k = r + 16 * s;
-        const double2 w = s_w512[k];
-        double xr_, xi_;
-        afp_real_post(zr[s], zi[s], c, d, w.x, w.y, xr_, xi_);
-        const double ss = xr_ * xr_ + xi_ * xi_;
-        const double lg = 0.5 * log(ss);
-        out[k] = lg;
-        if (WRITE_MAG) a.mag[frame * 257 + k] = sqrt(ss);
+      afp_fft16(zr, zi);
+      double* xr = s_xr + g * XF;
+      double* xi = s_xi + g * XF;
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const double2 w = s_tw256[p * 16 + r];
+        xr[p * XS + r] = zr[p] * w.x - zi[p] * w.y;
+        xi[p * XS + r] = zr[p] * w.y + zi[p] * w.x;
+      }
+    }
+    __syncwarp();
+    if (active) {
+      // step B: thread p = r transforms column p: Z[p + 16 s]
+      const double* xr = s_xr + g * XF + r * XS;
+      const double* xi = s_xi + g * XF + r * XS;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        zr[q] = xr[q];
+        zi[q] = xi[q];
+      }
+      afp_fft16(zr, zi);
+    }
+    // real-FFT split on pairs (k, 256-k), k = r + 16 s, s < 8: the partner
+    // Z[(256-k)&255] sits in lane (16-r)&15, register 15-s (r > 0) or (16-s)&15 (r == 0).
+    //   2Xe = Z[k] + conj(Zp), 2Xo = -i (Z[k] - conj(Zp)), P = W512^k * 2Xo
+    //   4|X[k]|^2 = |2Xe + P|^2,  4|X[256-k]|^2 = |2Xe - P|^2
+    {
+      double* out = a.logs + frame * AFP_NBINS;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        double c = __shfl_sync(0xffffffffu, zr[15 - s], src_lane);
+        double d = __shfl_sync(0xffffffffu, zi[15 - s], src_lane);
+        if (r == 0) {
+          c = zr[(16 - s) & 15];
+          d = zi[(16 - s) & 15];
+        }
+        if (active) {
+          const int k = r + 16 * s;
+          const double2 w = s_w512[k];
+          const double er = zr[s] + c, ei = zi[s] - d, orr = zi[s] + d, oi = c - zr[s];
+          const double pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
+          const double ar = er + pr, ai = ei + pi, br = er - pr, bi = ei - pi;
+          const double ssa = ar * ar + ai * ai;   // 4 |X[k]|^2
+          const double ssb = br * br + bi * bi;   // 4 |X[256-k]|^2
+          double la = half_log_quarter(ssa, s_logtab);
+          double lb = half_log_quarter(ssb, s_logtab);
+          if (is_special(ssa) || is_special(ssb)) {   // digital silence etc.: rare, off the hot path
+            la = half_log_quarter_slow(ssa);
+            lb = half_log_quarter_slow(ssb);
+          }
+          out[k] = la;
+          if (k != 0) out[256 - k] = lb; else a.nyq[frame] = lb;   // k == 0 pairs with the Nyquist bin
+          if (WRITE_MAG) {
+            a.mag[frame * 257 + k] = sqrt(0.25 * ssa);
+            a.mag[frame * 257 + 256 - k] = sqrt(0.25 * ssb);
+          }
+          vmax = fmax(vmax, fmax(ssa, ssb));
+          vmin = fmin(vmin, fmin(la, lb));
+          vsum += la + lb;
+        }
+      }
+      if (active && r == 0) {   // bin 128 pairs with itself
+        const double2 w = s_w512[128];
+        const double er = 2.0 * zr[8], orr = 2.0 * zi[8];   // ei = 0, oi = 0
+        const double ar = er + w.x * orr, ai = w.y * orr;
+        const double ss = ar * ar + ai * ai;
+        double lg = half_log_quarter(ss, s_logtab);
+        if (is_special(ss)) lg = half_log_quarter_slow(ss);
+        out[128] = lg;
+        if (WRITE_MAG) a.mag[frame * 257 + 128] = sqrt(0.25 * ss);
         vmax = fmax(vmax, ss);
         vmin = fmin(vmin, lg);
         vsum += lg;
       }
     }
-    if (active && r == 0) {   // Nyquist bin: X[256] = Re Z[0] - Im Z[0]
-      const double xn = zr[0] - zi[0];
-      const double ss = xn * xn;
-      const double lg = 0.5 * log(ss);
-      a.nyq[frame] = lg;
-      if (WRITE_MAG) a.mag[frame * 257 + 256] = sqrt(ss);
-      vmax = fmax(vmax, ss);
-      vmin = fmin(vmin, lg);
-      vsum += lg;
-    }
-  }
-  // deterministic CTA reduction of (max |S|^2, min log, sum log)
+    // deterministic CTA reduction of (max |S|^2, min log, sum log)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-  }
-  if ((tid & 31) == 0) {
-    s_red[(tid >> 5) * 3 + 0] = vmax;
-    s_red[(tid >> 5) * 3 + 1] = vmin;
-    s_red[(tid >> 5) * 3 + 2] = vsum;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double m = 0.0, mn = INFINITY, sm = 0.0;
-#pragma unroll
-    for (int w = 0; w < K1_THREADS / 32; ++w) {
-      m = fmax(m, s_red[w * 3 + 0]);
-      mn = fmin(mn, s_red[w * 3 + 1]);
-      sm += s_red[w * 3 + 2];
+    for (int o = 16; o > 0; o >>= 1) {
+      vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
     }
-    a.tile_stats[(size_t)tile * 3 + 0] = m;
-    a.tile_stats[(size_t)tile * 3 + 1] = mn;
-    a.tile_stats[(size_t)tile * 3 + 2] = sm;
+    if (lane == 0) {
+      s_red[(tid >> 5) * 3 + 0] = vmax;
+      s_red[(tid >> 5) * 3 + 1] = vmin;
+      s_red[(tid >> 5) * 3 + 2] = vsum;
+    }
+    __syncthreads();   // also: every thread is done with s_pcm[buf]
+    if (tid == 0) {
+      double m = 0.0, mn = INFINITY, sm = 0.0;
+#pragma unroll
+      for (int w = 0; w < K1_THREADS / 32; ++w) {
+        m = fmax(m, s_red[w * 3 + 0]);
+        mn = fmin(mn, s_red[w * 3 + 1]);
+        sm += s_red[w * 3 + 2];
+      }
+      a.tile_stats[(size_t)tile * 3 + 0] = 0.25 * m;
+      a.tile_stats[(size_t)tile * 3 + 1] = mn;
+      a.tile_stats[(size_t)tile * 3 + 2] = sm;
+    }
+    if (NBUF == 2) buf ^= 1;
+    cur = nxt;
+    if (tile + 2 * G < a.tile_end) nxt = make_tile<PcmT>(a, desc_nn, tile + 2 * G);
+    item_nn = item_n3;
+    if (NBUF == 1 && next < a.tile_end) stage_tile<PcmT>(a, cur, s_pcm, s_bar);
   }
 }
 
-constexpr size_t k1_smem_bytes(size_t pcm_elem) {
-  return 512 * 8 + 256 * 16 * 2 + 2 * FT * XF * 8 + 24 * 8 + 16 + (FT + 1) * 256 * pcm_elem;
+// tile -> item table (one thread per item)
+__global__ void afp_tile_table_kernel(const ItemDesc* items, int nitems, int32_t* tile_item) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nitems) return;
+  const ItemDesc it = items[i];
+  const int nt = (it.nframes + FT - 1) / FT;
+  for (int k = 0; k < nt; ++k) tile_item[it.tile_base + k] = i;
+}
+
+constexpr size_t k1_smem_bytes(size_t pcm_elem, int nbuf) {
+  return 512 * 8 + 256 * 16 * 2 + LOGTAB * 16 + 2 * FT * XF * 8 + 24 * 8 + 16 + nbuf * (FT + 1) * 256 * pcm_elem;
 }
 
 // ---- per-item statistics: floor, mean (audfprint_analyze.py:283-286) ----------
 // One CTA per item.  Fast path: no value below the floor -> mean from the tile
 // partial sums (fixed order, deterministic).  Slow path (digital silence etc.):
 // re-read the stored logs and sum max(L, floor).
-__global__ void __launch_bounds__(256) afp_stats_kernel(const ItemDesc* items, int nitems,
+__global__ void __launch_bounds__(256) afp_stats_kernel(const ItemDesc* items, int item0,
                                                         const double* tile_stats, const double* logs,
                                                         const double* nyq, ItemStats* out) {
   __shared__ double s_a[256], s_b[256], s_c[256];
-  const int item = blockIdx.x;
+  const int item = item0 + blockIdx.x;
   const ItemDesc it = items[item];
   const int tid = threadIdx.x;
   const int ntiles = (it.nframes + FT - 1) / FT;
@@ -317,24 +451,38 @@ __global__ void afp_sgram_kernel(const ItemDesc* items, const ItemStats* stats, 
 
 }  // namespace
 
-int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out) {
-  if (c->total_tiles == 0) return AFP_OK;
+int afp_launch_tile_table(afp_ctx* c) {
+  if (c->nitems == 0) return AFP_OK;
+  afp_tile_table_kernel<<<(c->nitems + 255) / 256, 256, 0, c->stream>>>(c->d_items.as<ItemDesc>(), c->nitems,
+                                                                       c->d_tile_item.as<int32_t>());
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches++;
+  return AFP_OK;
+}
+
+int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int64_t tile0, int64_t ntiles) {
+  if (ntiles <= 0) return AFP_OK;
   StftArgs a;
   a.pcm = pcm;
   a.items = c->d_items.as<ItemDesc>();
+  a.tile_item = c->d_tile_item.as<int32_t>();
   a.nitems = c->nitems;
-  a.window = c->d_window.as<double>();
-  a.w256 = c->d_twid.as<double2>();
+  a.tile_begin = (int)tile0;
+  a.tile_end = (int)(tile0 + ntiles);
+  a.window = c->d_window.as<double>() + (dtype == AFP_PCM_I16 ? AFP_N_FFT : 0);
+  a.tw256 = c->d_twid.as<double2>();
   a.w512 = c->d_twid.as<double2>() + 256;
+  a.logtab = c->d_twid.as<double2>() + 512;
   a.logs = c->d_logs.as<double>();
   a.nyq = c->d_nyq.as<double>();
   a.tile_stats = c->d_tile_stats.as<double>();
   a.mag = mag_out;
-  const dim3 grid((unsigned)c->total_tiles), block(K1_THREADS);
+  const int nctas = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * 2);
+  const dim3 grid((unsigned)nctas), block(K1_THREADS);
   cudaError_t e;
 #define LAUNCH(T, M)                                                                              \
   do {                                                                                            \
-    const size_t smem = k1_smem_bytes(sizeof(T));                                                 \
+    const size_t smem = k1_smem_bytes(sizeof(T), PcmTraits<T>::NBUF);                             \
     e = cudaFuncSetAttribute(afp_stft_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                              (int)smem);                                                          \
     if (e == cudaSuccess) afp_stft_kernel<T, M><<<grid, block, smem, c->stream>>>(a);             \
@@ -351,9 +499,9 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out) {
   return AFP_OK;
 }
 
-int afp_launch_stats(afp_ctx* c) {
-  if (c->nitems == 0) return AFP_OK;
-  afp_stats_kernel<<<c->nitems, 256, 0, c->stream>>>(c->d_items.as<ItemDesc>(), c->nitems,
+int afp_launch_stats(afp_ctx* c, int item0, int nitems) {
+  if (nitems <= 0) return AFP_OK;
+  afp_stats_kernel<<<nitems, 256, 0, c->stream>>>(c->d_items.as<ItemDesc>(), item0,
                                                      c->d_tile_stats.as<double>(), c->d_logs.as<double>(),
                                                      c->d_nyq.as<double>(), c->d_item_stats.as<ItemStats>());
   AFP_CUDA(c, cudaGetLastError());

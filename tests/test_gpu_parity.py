@@ -188,3 +188,27 @@ def test_match_file_level_api(tmp_path):
         an.wavfile2hashes(str(tmp_path / "missing.wav"))
     an.fail_on_error = False
     assert len(an.wavfile2hashes(str(tmp_path / "missing.wav"))) == 0
+
+
+def test_chunked_host_pipeline_equals_resident_path():
+    """>= 64 MB of host PCM takes the chunked copy/compute pipeline inside
+    afp_fingerprint_batch; it must give exactly what the device-resident path gives."""
+    import torch
+    base = [synth_track(3000 + i, 29.0 + 0.37 * i) for i in range(6)]
+    sigs = [base[i % 6][: len(base[i % 6]) - 17 * (i // 6)] for i in range(120)]
+    al = 8
+    lens = np.array([len(s) for s in sigs], np.int64)
+    starts = np.zeros(len(sigs) + 1, np.int64)
+    starts[1:] = np.cumsum((lens + al - 1) // al * al)
+    packed = np.zeros(int(starts[-1]) + al, np.int16)
+    for s, o in zip(sigs, starts[:-1]):
+        packed[o:o + len(s)] = s
+    assert packed.nbytes >= 64 << 20
+    an = Analyzer()
+    rows_h, off_h = an.fingerprint_packed(packed, starts, sample_lengths=lens)          # chunked
+    dev = torch.from_numpy(packed).cuda()
+    rows_d, off_d = an.fingerprint_packed(dev, starts, sample_lengths=lens)             # resident
+    assert np.array_equal(off_h, off_d) and np.array_equal(rows_h, rows_d)
+    for i in (0, 7, 119):
+        want = orc.fingerprint(pcm_to_float(sigs[i]))
+        assert np.array_equal(rows_h[off_h[i]:off_h[i + 1]], want)
