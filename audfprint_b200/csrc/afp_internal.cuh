@@ -125,6 +125,7 @@ struct afp_ctx {
   int32_t match_nq = 0;
   int64_t match_total_rows = -1;
   int32_t match_row_cap = 0;
+  uint64_t match_layout = 0;   // carve-up of d_mscratch whose counters/histograms are known to be zero
 };
 
 #define AFP_CUDA(ctx, call)                                                        \

@@ -19,7 +19,10 @@
 
 namespace {
 
-constexpr int MT = 256;   // threads per matching CTA
+constexpr int MT = 1024;          // threads per matching CTA (one CTA per SM, persistent over the queries)
+constexpr int NW = MT / 32;
+constexpr int ACAP = 1024;        // ids with raw > threshcount handled by the fast path
+constexpr int SLOT_SHIFT = 21;    // counter word = raw | (candidate slot + 1) << 21
 
 struct MatchArgs {
   const int32_t* q;        // [sum nq][2]
@@ -35,6 +38,7 @@ struct MatchArgs {
   uint2* hits;      int64_t hits_cap;     // (id, dt + bias)
   uint32_t* dlist;                        // distinct ids, hits_cap
   double* wtd;                            // weighted count per dlist entry, hits_cap
+  uint32_t* dts;                          // dt + bias of the candidates' hits, grouped per candidate, hits_cap
   uint32_t* counters;                     // nids
   int32_t* hist;    int hist_len;         // dtime histogram
   int32_t* filt;                          // local-max filtered copy
@@ -43,39 +47,53 @@ struct MatchArgs {
   int32_t* row_cnt;                       // [nqueries] rows produced (may exceed row_cap)
 };
 
-struct Key {
-  unsigned long long w;   // bit pattern of the (positive) weighted count
-  unsigned id;
-  bool valid;
-};
-__device__ __forceinline__ bool key_less(const Key& a, const Key& b) {   // a < b
-  if (!a.valid) return b.valid;
-  if (!b.valid) return false;
-  return a.w < b.w || (a.w == b.w && a.id < b.id);
+// candidate order: (weighted count desc, id desc); keys are (bits of the positive double, id)
+__device__ __forceinline__ bool key_gt(unsigned long long w1, unsigned i1, unsigned long long w2, unsigned i2) {
+  return w1 > w2 || (w1 == w2 && i1 > i2);
 }
 
-__device__ Key block_max_key(Key k, Key* s_keys) {
-  const int tid = threadIdx.x;
+struct Shared {
+  unsigned long long a_w[ACAP];
+  unsigned a_id[ACAP];
+  unsigned a_raw[ACAP];
+  int a_rank[ACAP];      // bucket counts, then rank of A[j] among ALL distinct ids
+  int loff[ACAP];        // start of candidate j's dt list
+  int cur[ACAP];         // fill cursor of candidate j's dt list
+  unsigned char pass[ACAP];
+  int wsum[NW];
+  int val[NW], idx[NW];
+  unsigned long long kw[NW];
+  unsigned kid[NW];
+  unsigned nhits, ndist, nabove;
+  int dmin, dmax, nrows, ncand;
+};
+
+// inclusive scan of one int per thread over the CTA (MT threads)
+__device__ __forceinline__ int block_scan_incl(int v, int* wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Key other;
-    other.w = __shfl_xor_sync(0xffffffffu, k.w, o);
-    other.id = __shfl_xor_sync(0xffffffffu, k.id, o);
-    other.valid = __shfl_xor_sync(0xffffffffu, (int)k.valid, o) != 0;
-    if (key_less(k, other)) k = other;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
   }
   __syncthreads();
-  if ((tid & 31) == 0) s_keys[tid >> 5] = k;
+  if (lane == 31) wsum[warp] = v;
   __syncthreads();
-  Key best = s_keys[0];
-  for (int w = 1; w < MT / 32; ++w)
-    if (key_less(best, s_keys[w])) best = s_keys[w];
-  return best;
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  return v + (warp ? wsum[warp - 1] : 0);
 }
 
-// (value desc, index asc) arg-max over the filtered histogram == np.argmax (first max)
-__device__ void block_argmax(const int32_t* f, int lo, int hi, int* s_val, int* s_idx, int& best_v,
-                             int& best_i) {
+// (value desc, index asc) arg-max over f[lo..hi] == np.argmax (first max)
+__device__ void block_argmax(const int32_t* f, int lo, int hi, Shared& sh, int& best_v, int& best_i) {
   const int tid = threadIdx.x;
   int v = -1, ix = 0x7fffffff;
   for (int i = lo + tid; i <= hi; i += MT) {
@@ -89,97 +107,289 @@ __device__ void block_argmax(const int32_t* f, int lo, int hi, int* s_val, int* 
     if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
   }
   __syncthreads();
-  if ((tid & 31) == 0) { s_val[tid >> 5] = v; s_idx[tid >> 5] = ix; }
+  if ((tid & 31) == 0) { sh.val[tid >> 5] = v; sh.idx[tid >> 5] = ix; }
   __syncthreads();
-  best_v = s_val[0];
-  best_i = s_idx[0];
-  for (int w = 1; w < MT / 32; ++w)
-    if (s_val[w] > best_v || (s_val[w] == best_v && s_idx[w] < best_i)) { best_v = s_val[w]; best_i = s_idx[w]; }
+  best_v = sh.val[0];
+  best_i = sh.idx[0];
+  for (int w = 1; w < NW; ++w)
+    if (sh.val[w] > best_v || (sh.val[w] == best_v && sh.idx[w] < best_i)) { best_v = sh.val[w]; best_i = sh.idx[w]; }
+}
+
+// Histogram-mode search of one candidate (audfprint_match.py:284-311) given lo/hi of its
+// (already filled) dense histogram; emits rows, restores hist to zero.
+__device__ void candidate_modes(const MatchArgs& a, Shared& sh, int32_t* hist, int32_t* filt, int lo, int hi,
+                                unsigned id, int raw, int rank, int32_t* qrows) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // keep_local_maxes (:70-75, locmax :51-67); zero-extended ends are equivalent
+  for (int i = lo + tid; i <= hi; i += MT) {
+    const int v = __ldcg(hist + i), l = __ldcg(hist + i - 1), r = __ldcg(hist + i + 1);
+    filt[i] = (v >= l && r < v) ? v : 0;
+  }
+  __syncthreads();
+  int found = 0;
+  while (true) {
+    int bv, bi;
+    block_argmax(filt, lo, hi, sh, bv, bi);   // :290 np.argmax = first max
+    if (bv <= a.thresh) break;                // :291
+    // :295 count over +-window (hist is zero outside the touched range)
+    int part = 0;
+    for (int t2 = tid; t2 <= 2 * a.window; t2 += MT) part += __ldcg(hist + bi - a.window + t2);
+    part = __reduce_add_sync(0xffffffffu, part);
+    __syncthreads();
+    if (lane == 0) sh.val[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      int count = 0;
+      for (int w = 0; w < NW; ++w) count += sh.val[w];
+      const int nr = sh.nrows;
+      if (nr < a.row_cap) {
+        int32_t* row = qrows + (size_t)nr * 7;
+        row[0] = (int32_t)id; row[1] = count; row[2] = bi - a.bias; row[3] = raw;
+        row[4] = rank; row[5] = 0; row[6] = 0;                      // :300-301
+      }
+      sh.nrows = nr + 1;
+    }
+    for (int t2 = tid; t2 <= 2 * a.window; t2 += MT) {              // :307-308
+      const int i = bi - a.window + t2;
+      if (i >= lo && i <= hi) filt[i] = 0;
+    }
+    __syncthreads();
+    ++found;
+    if (found > a.maxalign) break;                                   // :309-311
+  }
+  __syncthreads();
+  for (int i = lo + tid; i <= hi; i += MT) hist[i] = 0;              // restore the scratch
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
-  __shared__ Key s_keys[MT / 32];
-  __shared__ int s_val[MT / 32], s_idx[MT / 32];
-  __shared__ unsigned s_nhits, s_ndist, s_nabove;
-  __shared__ int s_dmin, s_dmax, s_nrows;
+  __shared__ Shared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint2* hits = a.hits + (size_t)blockIdx.x * a.hits_cap;
   uint32_t* dlist = a.dlist + (size_t)blockIdx.x * a.hits_cap;
   double* wtd = a.wtd + (size_t)blockIdx.x * a.hits_cap;
+  uint32_t* dts = a.dts + (size_t)blockIdx.x * a.hits_cap;
   uint32_t* cnt = a.counters + (size_t)blockIdx.x * a.nids;
   int32_t* hist = a.hist + (size_t)blockIdx.x * a.hist_len;
   int32_t* filt = a.filt + (size_t)blockIdx.x * a.hist_len;
   const uint32_t hmask = (1u << a.hashbits) - 1u, tmask = (1u << a.mtb) - 1u;
+  const uint32_t RAWMASK = (1u << SLOT_SHIFT) - 1u;
 
   for (int qi = blockIdx.x; qi < a.nqueries; qi += gridDim.x) {
     const int64_t q0 = a.qoff[qi];
     const int nq = (int)(a.qoff[qi + 1] - q0);
-    if (tid == 0) { s_nhits = 0; s_ndist = 0; s_nabove = 0; s_nrows = 0; }
+    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; sh.ncand = 0; }
     __syncthreads();
-    // ---- probe (hash_table.py:162-173): one warp per query row, lanes over slots
-    for (int r = warp; r < nq; r += MT / 32) {
+    // ---- probe (hash_table.py:162-173): one warp per query row, every lane owns up to 4 slots;
+    // all table loads and counter atomics of a row are in flight together
+    for (int r = warp; r < nq; r += NW) {
       const int qt = a.q[2 * (q0 + r)];
       const uint32_t b = (uint32_t)a.q[2 * (q0 + r) + 1] & hmask;
       const int n = min(a.depth, a.counts[b]);
-      unsigned basepos = 0;
-      if (lane == 0 && n > 0) basepos = atomicAdd(&s_nhits, (unsigned)n);
-      basepos = __shfl_sync(0xffffffffu, basepos, 0);
       const uint32_t* row = a.table + (size_t)b * a.depth;
-      for (int s = lane; s < n; s += 32) {
-        const uint32_t v = row[s];
-        const uint32_t id = (v >> a.mtb) - 1u;
-        const int dt = (int)(v & tmask) - qt;
-        hits[basepos + s] = make_uint2(id, (unsigned)(dt + a.bias));
-        if (id < (uint32_t)a.nids) {
-          const unsigned old = atomicAdd(&cnt[id], 1u);
-          if (old == 0) dlist[atomicAdd(&s_ndist, 1u)] = id;
+      for (int s0 = 0; s0 < n; s0 += 128) {
+        uint32_t v[4], old[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (s0 + 32 * u + lane < n) ? row[s0 + 32 * u + lane] : 0u;
+        const int chunk = min(128, n - s0);
+        unsigned basepos = 0;
+        if (lane == 0) basepos = atomicAdd(&sh.nhits, (unsigned)chunk);
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          old[u] = 1u;
+          if (s0 + 32 * u + lane < n) {
+            const uint32_t id = (v[u] >> a.mtb) - 1u;
+            hits[basepos + 32 * u + lane] = make_uint2(id, (unsigned)((int)(v[u] & tmask) - qt + a.bias));
+            if (id < (uint32_t)a.nids) old[u] = atomicAdd(&cnt[id], 1u);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // first touch of an id -> distinct list (warp-aggregated append)
+          const bool first = old[u] == 0u;
+          const unsigned fm = __ballot_sync(0xffffffffu, first);
+          if (fm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&sh.ndist, (unsigned)__popc(fm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (first) dlist[base + __popc(fm & ((1u << lane) - 1u))] = (v[u] >> a.mtb) - 1u;
+          }
         }
       }
     }
     __syncthreads();
-    const int nhits = (int)s_nhits, ndist = (int)s_ndist;
-    // ---- weighted counts, number of ids above threshold (audfprint_match.py:132-144)
-    {
-      unsigned above = 0;
-      for (int i = tid; i < ndist; i += MT) {
-        const uint32_t id = dlist[i];
-        const uint32_t raw = cnt[id];
-        wtd[i] = (double)raw / (double)a.hpi[id];
-        above += raw > (uint32_t)a.thresh ? 1u : 0u;
+    const int nhits = (int)sh.nhits, ndist = (int)sh.ndist;
+    // ---- weighted counts; ids above threshold go to A (audfprint_match.py:132-144)
+    for (int i0 = 0; i0 < ndist; i0 += MT) {
+      const int i = i0 + tid;
+      bool ab = false;
+      unsigned id = 0, raw = 0;
+      double w = 0.0;
+      if (i < ndist) {
+        id = dlist[i];
+        raw = __ldcg(cnt + id);
+        w = (double)raw / (double)a.hpi[id];
+        wtd[i] = w;
+        ab = raw > (uint32_t)a.thresh;
       }
-      above = __reduce_add_sync(0xffffffffu, above);
-      if (lane == 0 && above) atomicAdd(&s_nabove, above);
+      const unsigned am = __ballot_sync(0xffffffffu, ab);
+      if (am) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&sh.nabove, (unsigned)__popc(am));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned pos = base + __popc(am & ((1u << lane) - 1u));
+        if (ab && pos < ACAP) {
+          sh.a_w[pos] = (unsigned long long)__double_as_longlong(w);
+          sh.a_id[pos] = id;
+          sh.a_raw[pos] = raw;
+        }
+      }
     }
     __syncthreads();
-    const int maxdepth = min((int)s_nabove, a.sdepth);
+    const int nabove = (int)sh.nabove;
+    const int maxdepth = min(nabove, a.sdepth);
     int32_t* qrows = a.rows + (size_t)qi * a.row_cap * 7;
-    Key prev;
-    prev.valid = false; prev.w = ~0ull; prev.id = ~0u;
-    for (int rank = 0; rank < maxdepth; ++rank) {
-      // ---- next candidate by (weight desc, id desc)
-      Key best;
-      best.valid = false; best.w = 0; best.id = 0;
-      for (int i = tid; i < ndist; i += MT) {
-        Key k;
-        k.w = (unsigned long long)__double_as_longlong(wtd[i]);
-        k.id = dlist[i];
-        k.valid = true;
-        const bool below_prev = !prev.valid || (k.w < prev.w || (k.w == prev.w && k.id < prev.id));
-        if (below_prev && key_less(best, k)) best = k;
-      }
-      best = block_max_key(best, s_keys);
-      if (!best.valid) break;
-      prev = best;
-      const uint32_t id = best.id;
-      const int raw = (int)cnt[id];
-      // ---- dtime histogram of this id (audfprint_match.py:284)
-      if (tid == 0) { s_dmin = 0x7fffffff; s_dmax = -1; }
+
+    if (maxdepth > 0 && nabove <= ACAP) {
+      // ---- fast path.  Only ids with raw > threshcount can produce rows, but their rank
+      // is their position among ALL distinct ids in (weight desc, id desc) order.
+      int n2 = 1;
+      while (n2 < nabove) n2 <<= 1;
+      for (int i = nabove + tid; i < n2; i += MT) { sh.a_w[i] = 0ull; sh.a_id[i] = 0u; sh.a_raw[i] = 0u; }
+      __syncthreads();
+      for (int k = 2; k <= n2; k <<= 1)          // bitonic sort of A, descending
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < n2; i += MT) {
+            const int l = i ^ j;
+            if (l > i) {
+              const bool desc = (i & k) == 0;
+              const bool gt = key_gt(sh.a_w[i], sh.a_id[i], sh.a_w[l], sh.a_id[l]);
+              if (gt != desc) {
+                const unsigned long long tw = sh.a_w[i]; sh.a_w[i] = sh.a_w[l]; sh.a_w[l] = tw;
+                const unsigned ti = sh.a_id[i]; sh.a_id[i] = sh.a_id[l]; sh.a_id[l] = ti;
+                const unsigned tr = sh.a_raw[i]; sh.a_raw[i] = sh.a_raw[l]; sh.a_raw[l] = tr;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < nabove; i += MT) sh.a_rank[i] = 0;
       __syncthreads();
       {
+        const unsigned long long wmin = sh.a_w[nabove - 1];
+        const unsigned idmin = sh.a_id[nabove - 1];
+        for (int i = tid; i < ndist; i += MT) {
+          const unsigned long long w = (unsigned long long)__double_as_longlong(wtd[i]);
+          if (w < wmin) continue;
+          const unsigned id = dlist[i];
+          if (!key_gt(w, id, wmin, idmin)) continue;
+          int lo = 0, hi = nabove;      // ge = #{j : A[j] >= key}; d outranks every A[j], j >= ge
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (!key_gt(w, id, sh.a_w[mid], sh.a_id[mid])) lo = mid + 1; else hi = mid;
+          }
+          if (lo < nabove) atomicAdd(&sh.a_rank[lo], 1);
+        }
+      }
+      __syncthreads();
+      {   // rank(A[j]) = inclusive prefix of the buckets; candidates are those with rank < maxdepth
+        const int b = (tid < nabove) ? sh.a_rank[tid] : 0;
+        const int rk = block_scan_incl(b, sh.wsum);
+        if (tid < nabove) sh.a_rank[tid] = rk;
+        const bool cand = tid < nabove && rk < maxdepth;
+        const int craw = cand ? (int)sh.a_raw[tid] : 0;
+        const int lend = block_scan_incl(craw, sh.wsum);       // ranks increase with j: candidates are a prefix
+        if (cand) {
+          sh.loff[tid] = lend - craw;
+          sh.cur[tid] = 0;
+          cnt[sh.a_id[tid]] = sh.a_raw[tid] | ((unsigned)(tid + 1) << SLOT_SHIFT);
+          atomicAdd(&sh.ncand, 1);
+        }
+      }
+      __syncthreads();
+      const int ncand = sh.ncand;
+      // ---- one pass over the hits: route the hits of candidates to their dt lists
+      for (int i = tid; i < nhits; i += MT) {
+        const uint2 h = hits[i];
+        if (h.x >= (uint32_t)a.nids) continue;
+        const unsigned c = __ldcg(cnt + h.x) >> SLOT_SHIFT;
+        if (c) dts[sh.loff[c - 1] + atomicAdd(&sh.cur[c - 1], 1)] = h.y;
+      }
+      __syncthreads();
+      // ---- quick filter, one warp per candidate: a row needs a dtime bin > threshcount (:291)
+      for (int j = warp; j < ncand; j += NW) {
+        const int n = (int)sh.a_raw[j];
+        const uint32_t* L = dts + sh.loff[j];
+        int best = 0;
+        for (int i = lane; i < n; i += 32) {
+          const uint32_t me = L[i];
+          int c = 0;
+          for (int k = 0; k < n; ++k) c += (L[k] == me) ? 1 : 0;
+          best = max(best, c);
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (lane == 0) sh.pass[j] = best > a.thresh;
+      }
+      __syncthreads();
+      // ---- full mode search of the surviving candidates, in rank order
+      for (int j = 0; j < ncand; ++j) {
+        if (!sh.pass[j]) continue;          // uniform
+        const int n = (int)sh.a_raw[j];
+        const uint32_t* L = dts + sh.loff[j];
+        if (tid == 0) { sh.dmin = 0x7fffffff; sh.dmax = -1; }
+        __syncthreads();
+        int dmin = 0x7fffffff, dmax = -1;
+        for (int i = tid; i < n; i += MT) {
+          const int d = (int)L[i];
+          atomicAdd(&hist[d], 1);
+          dmin = min(dmin, d);
+          dmax = max(dmax, d);
+        }
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0 && dmax >= 0) { atomicMin(&sh.dmin, dmin); atomicMax(&sh.dmax, dmax); }
+        __syncthreads();
+        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, sh.a_id[j], n, sh.a_rank[j], qrows);
+      }
+    } else if (maxdepth > 0) {
+      // ---- slow path (more than ACAP ids above threshold): one pass over the distinct
+      // ids and one over the hits per candidate
+      unsigned long long pw = ~0ull;
+      unsigned pid = ~0u;
+      bool have_prev = false;
+      for (int rank = 0; rank < maxdepth; ++rank) {
+        unsigned long long bw = 0ull;
+        unsigned bid = 0u;
+        bool bvld = false;
+        for (int i = tid; i < ndist; i += MT) {
+          const unsigned long long w = (unsigned long long)__double_as_longlong(wtd[i]);
+          const unsigned id = dlist[i];
+          if (have_prev && !key_gt(pw, pid, w, id)) continue;
+          if (!bvld || key_gt(w, id, bw, bid)) { bw = w; bid = id; bvld = true; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+          const unsigned oid = __shfl_xor_sync(0xffffffffu, bid, o);
+          const bool ov = __shfl_xor_sync(0xffffffffu, (int)bvld, o) != 0;
+          if (ov && (!bvld || key_gt(ow, oid, bw, bid))) { bw = ow; bid = oid; bvld = true; }
+        }
+        __syncthreads();
+        if (lane == 0) { sh.kw[warp] = bw; sh.kid[warp] = bid; sh.val[warp] = bvld; }
+        __syncthreads();
+        bvld = false;
+        for (int w = 0; w < NW; ++w)
+          if (sh.val[w] && (!bvld || key_gt(sh.kw[w], sh.kid[w], bw, bid))) { bw = sh.kw[w]; bid = sh.kid[w]; bvld = true; }
+        if (!bvld) break;
+        pw = bw; pid = bid; have_prev = true;
+        const int raw = (int)(__ldcg(cnt + bid) & RAWMASK);
+        if (raw <= a.thresh) continue;      // cannot yield a row (:291), but keeps its rank
+        if (tid == 0) { sh.dmin = 0x7fffffff; sh.dmax = -1; }
+        __syncthreads();
         int dmin = 0x7fffffff, dmax = -1;
         for (int i = tid; i < nhits; i += MT) {
           const uint2 h = hits[i];
-          if (h.x == id) {
+          if (h.x == bid) {
             atomicAdd(&hist[h.y], 1);
             dmin = min(dmin, (int)h.y);
             dmax = max(dmax, (int)h.y);
@@ -187,56 +397,15 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         }
         dmin = __reduce_min_sync(0xffffffffu, dmin);
         dmax = __reduce_max_sync(0xffffffffu, dmax);
-        if (lane == 0 && dmax >= 0) { atomicMin(&s_dmin, dmin); atomicMax(&s_dmax, dmax); }
-      }
-      __syncthreads();
-      const int lo = s_dmin, hi = s_dmax;
-      // keep_local_maxes (:70-75, locmax :51-67); zero-extended ends are equivalent
-      for (int i = lo + tid; i <= hi; i += MT) {
-        const int v = hist[i], l = hist[i - 1], r = hist[i + 1];
-        filt[i] = (v >= l && r < v) ? v : 0;
-      }
-      __syncthreads();
-      int found = 0;
-      while (true) {
-        int bv, bi;
-        block_argmax(filt, lo, hi, s_val, s_idx, bv, bi);   // :290 np.argmax = first max
-        if (bv <= a.thresh) break;                          // :291
-        // :295 count over +-window (hist is zero outside the touched range)
-        int part = 0;
-        if (tid <= 2 * a.window) part = hist[bi - a.window + tid];
-        for (int t2 = tid + MT; t2 <= 2 * a.window; t2 += MT) part += hist[bi - a.window + t2];
-        part = __reduce_add_sync(0xffffffffu, part);
+        if (lane == 0 && dmax >= 0) { atomicMin(&sh.dmin, dmin); atomicMax(&sh.dmax, dmax); }
         __syncthreads();
-        if (lane == 0) s_val[warp] = part;
-        __syncthreads();
-        if (tid == 0) {
-          int count = 0;
-          for (int w = 0; w < MT / 32; ++w) count += s_val[w];
-          const int nr = s_nrows;
-          if (nr < a.row_cap) {
-            int32_t* row = qrows + (size_t)nr * 7;
-            row[0] = (int32_t)id; row[1] = count; row[2] = bi - a.bias; row[3] = raw;
-            row[4] = rank; row[5] = 0; row[6] = 0;                      // :300-301
-          }
-          s_nrows = nr + 1;
-        }
-        for (int t2 = tid; t2 <= 2 * a.window; t2 += MT) {              // :307-308
-          const int i = bi - a.window + t2;
-          if (i >= lo && i <= hi) filt[i] = 0;
-        }
-        __syncthreads();
-        ++found;
-        if (found > a.maxalign) break;                                   // :309-311
+        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, bid, raw, rank, qrows);
       }
-      __syncthreads();
-      for (int i = lo + tid; i <= hi; i += MT) hist[i] = 0;              // restore the scratch
-      __syncthreads();
     }
     // ---- restore the counter array by replaying the distinct ids
     __syncthreads();
     for (int i = tid; i < ndist; i += MT) cnt[dlist[i]] = 0;
-    if (tid == 0) a.row_cnt[qi] = s_nrows;
+    if (tid == 0) a.row_cnt[qi] = sh.nrows;
     __syncthreads();
   }
 }
@@ -458,9 +627,8 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (h_mm[1] < 0) AFP_FAIL(c, AFP_ERR_INVALID, "negative query time");
 
-  cudaDeviceProp prop;
-  AFP_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
-  const int nctas = (int)std::min<int64_t>(nqueries, (int64_t)prop.multiProcessorCount * 2);
+  // persistent grid; a fixed CTA count keeps the scratch layout (and its zeroed state) reusable
+  const int nctas = c->num_sms;
   MatchArgs a;
   a.q = dq;
   a.qoff = c->d_qoff.as<int64_t>();
@@ -482,8 +650,10 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.row_cap = 256;
   const char* env = getenv("AFP_MATCH_ROW_CAP");
   if (env && atoi(env) > 0) a.row_cap = atoi(env);
-  const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(double)) +
-                         (size_t)a.nids * sizeof(uint32_t) + (size_t)a.hist_len * 2 * sizeof(int32_t) + 64;
+  if (a.hits_cap >= ((int64_t)1 << SLOT_SHIFT))
+    AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large: rows * depth must stay below 2^21");
+  const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + 2 * sizeof(uint32_t) + sizeof(double)) +
+                         (size_t)a.nids * sizeof(uint32_t) + (size_t)a.hist_len * 2 * sizeof(int32_t) + 256;
   const size_t before = c->d_mscratch.cap;
   AFP_CUDA(c, c->d_mscratch.reserve(per_cta * (size_t)nctas + 1024));
   AFP_CUDA(c, c->d_mrows.reserve(sizeof(int32_t) * 7 * (size_t)a.row_cap * (size_t)nqueries));
@@ -497,12 +667,19 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.hits = (uint2*)carve(sizeof(uint2) * a.hits_cap * nctas);
   a.wtd = (double*)carve(sizeof(double) * a.hits_cap * nctas);
   a.dlist = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
+  a.dts = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
   char* zero0 = base;
   a.counters = (uint32_t*)carve(sizeof(uint32_t) * (size_t)a.nids * nctas);
   a.hist = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
   a.filt = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
-  (void)before;
-  AFP_CUDA(c, cudaMemsetAsync(zero0, 0, (size_t)(base - zero0), c->stream));
+  // counters and histograms are left zeroed by the kernel itself: clear them only when the
+  // carve-up changed (or the buffer moved)
+  const uint64_t layout = (uint64_t)a.hits_cap * 1000003ull ^ (uint64_t)a.nids * 7919ull ^ (uint64_t)a.hist_len * 31ull ^
+                          (uint64_t)(uintptr_t)c->d_mscratch.p ^ (uint64_t)before;
+  if (layout != c->match_layout) {
+    AFP_CUDA(c, cudaMemsetAsync(zero0, 0, (size_t)(base - zero0), c->stream));
+    c->match_layout = layout;
+  }
   a.rows = c->d_mrows.as<int32_t>();
   a.row_cnt = c->d_mrow_cnt.as<int32_t>();
   c->match_row_cap = a.row_cap;

@@ -83,6 +83,52 @@ def cpu_pass(pool, n):
     return time.perf_counter() - t0, out
 
 
+# ---------------------------------------------------------------- match workload (BASELINE configs[2])
+_TABLE = None       # (table, counts, hashbits, depth, maxtimebits, hashesperid) for forked CPU workers
+_QUERIES = None
+
+
+def _gen_query(args):
+    j, ntracks, first_seed, secs, qsecs, sigma = args
+    from audfprint_b200.synth import synth_track, synth_query
+    trk = j % ntracks
+    pcm, off = synth_query(synth_track(first_seed + trk, secs), j, seconds=qsecs, noise_sigma=sigma)
+    return pcm, trk, off
+
+
+def build_big_table(track_rows, track_off, nids, hashbits=20, depth=100, maxtimebits=12, seed=12345):
+    """plant the real hashes of the queried tracks in store order,
+    then fill every bucket to `depth` with uniform-random (id, time) distractors.  Returns the
+    reference-format arrays; the SAME arrays feed the CPU oracle and the GPU."""
+    rng = np.random.default_rng(seed)
+    nb = 1 << hashbits
+    ntracks = len(track_off) - 1
+    ids = (np.arange(ntracks, dtype=np.int64) * (nids // ntracks))            # real tracks spread over the id space
+    table = ((rng.integers(1, nids + 1, size=(nb, depth), dtype=np.int64) << maxtimebits)
+             + rng.integers(0, 1292, size=(nb, depth), dtype=np.int64)).astype(np.uint32)
+    h = (track_rows[:, 1].astype(np.int64)) & (nb - 1)
+    t = track_rows[:, 0].astype(np.int64) & ((1 << maxtimebits) - 1)
+    tid = np.repeat(ids, np.diff(track_off))
+    vals = (((tid + 1) << maxtimebits) + t).astype(np.uint32)
+    order = np.argsort(h, kind="stable")
+    hs = h[order]
+    first = np.r_[True, hs[1:] != hs[:-1]]
+    start = np.maximum.accumulate(np.where(first, np.arange(len(hs)), 0))
+    slot = np.arange(len(hs)) - start
+    keep = slot < depth
+    table[hs[keep], slot[keep]] = vals[order][keep]
+    counts = np.full(nb, depth, np.int32)
+    hpi = np.bincount((table >> maxtimebits).astype(np.int64).ravel() - 1, minlength=nids).astype(np.uint32)
+    return table, counts, hashbits, depth, maxtimebits, hpi, ids
+
+
+def _cpu_match(i):
+    from oracle import afp_oracle as orc
+    table, counts, hashbits, depth, mtb, hpi = _TABLE
+    return orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, _QUERIES[i], window=2, threshcount=5,
+                            search_depth=100)
+
+
 # ---------------------------------------------------------------- clocks sampler
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -128,6 +174,108 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream):
+    """BASELINE configs[2]: 10 s noisy excerpts (4 shifts) against a 1M-id device-resident
+    table (2^20 buckets x 100, every bucket full).  Reports match-only queries/s with the
+    query hashes resident on the device, the same through host buffers, and audio->result."""
+    global _TABLE, _QUERIES
+    import torch
+    from audfprint_b200 import Analyzer, HashTable, Matcher
+    nq = len(queries)
+    table, counts, hashbits, depth, mtb, hpi, ids = build_big_table(rows, roff, a.match_ids)
+    ht = HashTable(hashbits=hashbits, depth=1, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid, ht.depth = table, counts, hpi, depth
+    ht.names = [None] * a.match_ids
+    qan = Analyzer(device=an.device)
+    qan.shifts = 4
+    qpcm = [q[0] for q in queries]
+    stride = (max(len(p) for p in qpcm) + 7) // 8 * 8
+    hq = torch.zeros(nq * stride + 8, dtype=torch.int16).pin_memory()
+    hqn = hq.numpy()
+    for i, p in enumerate(qpcm):
+        hqn[i * stride:i * stride + len(p)] = p
+    qoffs = np.arange(nq + 1, dtype=np.int64) * stride
+    qlens = np.array([len(p) for p in qpcm], np.int64)
+    t0 = time.perf_counter()
+    qrows, qoff = qan.fingerprint_packed(hqn, qoffs, sample_lengths=qlens)
+    torch.cuda.synchronize()
+    fp_s = time.perf_counter() - t0
+    m = Matcher()
+    m.window = 2                      # CLI default --match-win 2 (audfprint.py:363)
+    for _ in range(2):
+        res = m.match_batch(ht, (qrows, qoff))
+    # --- match only, host hashes in / rows out (includes H2D of the query hashes, D2H of rows)
+    steps = 5
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = m.match_batch(ht, (qrows, qoff))
+    torch.cuda.synchronize()
+    host_s = (time.perf_counter() - t0) / steps
+    # --- match only, query hashes resident on the device, rows left on the device
+    import ctypes as C
+    dq = torch.from_numpy(qrows).cuda()
+    p = m._params()
+    tot = C.c_int64(0)
+    qoffp = np.ascontiguousarray(qoff).ctypes.data_as(C.POINTER(C.c_int64))
+
+    def dev_step():
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(p), C.byref(tot)))
+    for _ in range(2):
+        dev_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        dev_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3 / steps
+    # --- audio -> result (fingerprint 4 shifts + match), host PCM in
+    t0 = time.perf_counter()
+    r2, o2 = qan.fingerprint_packed(hqn, qoffs, sample_lengths=qlens)
+    res2 = m.match_batch(ht, (r2, o2))
+    torch.cuda.synchronize()
+    audio_s = time.perf_counter() - t0
+    truth = np.array([[ids[q[1]], q[2] // 256] for q in queries])
+    top = np.array([[r[0, 0], r[0, 2]] if len(r) else [-1, 0] for r in res])
+    correct = int(np.sum((top[:, 0] == truth[:, 0]) & (np.abs(top[:, 1] - truth[:, 1]) <= 1)))
+    nqh = int(qoff[-1])
+    nprobe = 12 * nqh + 4 * nqh * depth + 28 * sum(len(r) for r in res)      # SURVEY.md §8d B_m
+    out = {"metric": "match_queries_per_sec", "queries": nq, "table": "2^%d buckets x %d, %d ids, every bucket "
+           "full (SURVEY.md 8d config 3)" % (hashbits, depth, a.match_ids), "query_hashes": nqh,
+           "value": nq / dev_s, "unit": "queries/s", "ms_per_step": dev_s * 1e3,
+           "e2e": {"value": nq / host_s, "unit": "queries/s", "h2d_bytes_per_step": int(qrows.nbytes + qoff.nbytes),
+                   "d2h_bytes_per_step": int(sum(r.nbytes for r in res) + qoff.nbytes)},
+           "audio_to_result": {"value": nq / audio_s, "unit": "queries/s",
+                               "fingerprint_only_s": fp_s, "note": "10 s int16 PCM in (4 shifts) -> top rows out"},
+           "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": nprobe,
+                        "achieved": nprobe / dev_s / 1e9, "unit": "GB/s", "peak": measured_peaks()[0],
+                        "frac": nprobe / dev_s / 1e9 / measured_peaks()[0]},
+           "top1_correct": correct, "cpu_baseline": None, "parity": None}
+    if want_cpu:
+        ns = min(a.match_cpu_sample, nq)
+        _TABLE = (table, counts, hashbits, depth, mtb, hpi)
+        _QUERIES = [qrows[qoff[i]:qoff[i + 1]] for i in range(ns)]
+        mp_pool = mp.get_context("fork").Pool(min(cores, ns), initializer=_worker_init)
+        mp_pool.map(_cpu_match, range(min(cores, ns)), chunksize=1)
+        t0 = time.perf_counter()
+        want = mp_pool.map(_cpu_match, range(ns), chunksize=1)
+        dt = time.perf_counter() - t0
+        mp_pool.close()
+        bad = 0
+        for i in range(ns):
+            g = res[i]
+            w = want[i]
+            if not (g.shape == w.shape and sorted(map(tuple, g)) == sorted(map(tuple, w))):
+                bad += 1
+        out["cpu_baseline"] = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": "%d of the %d queries, oracle port (Python loop over query hashes as "
+                                         "the reference) on a %d-process pool, %.1f s wall" % (ns, nq, min(cores, ns), dt)}
+        out["parity"] = {"queries_checked": ns, "queries_mismatched": bad}
+    return out
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -146,6 +294,10 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--cpu-sample", type=int, default=512, help="files in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--match-queries", type=int, default=4096,
+                    help="queries of the match workload (0 = skip; BASELINE configs[2] uses 10000)")
+    ap.add_argument("--match-ids", type=int, default=1000000)
+    ap.add_argument("--match-cpu-sample", type=int, default=128)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,6 +345,11 @@ def main():
 
     # ------------------------------------------------------------ our arm
     tracks = make_tracks(pool, rank * a.files, a.files, a.seconds)
+    do_match = a.match_queries > 0 and world == 1
+    queries = None
+    if do_match:
+        queries = pool.map(_gen_query, [(j, a.files, rank * a.files, a.seconds, 10.0, 0.02)
+                                        for j in range(a.match_queries)], chunksize=16)
     pool.close()
     want_cpu = rank == 0 and world == 1 and not a.no_cpu_baseline
     cpool = cpu_pool(tracks[:min(a.cpu_sample, a.files)], cores) if want_cpu else None
@@ -285,6 +442,10 @@ def main():
                "sample": "%d of the %d files (%.0f audio-s), oracle port on a %d-process pool, %.1f s wall"
                          % (ns, a.files, ns * a.seconds, cores, dt)}
 
+    match = None
+    if do_match:
+        match = bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream)
+
     if rank == 0:
         peak, which = measured_peaks()
         T = 1 + nsamp // 256
@@ -313,7 +474,7 @@ def main():
                "stages_ms": {"h2d": float(stages[0]), "k1_stft_log": float(stages[1]),
                              "stats": float(stages[2]), "k2_peaks": float(stages[3]),
                              "k3_hashes": float(stages[4])},
-               "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity}
+               "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity, "match": match}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

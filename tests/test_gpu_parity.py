@@ -212,3 +212,28 @@ def test_chunked_host_pipeline_equals_resident_path():
     for i in (0, 7, 119):
         want = orc.fingerprint(pcm_to_float(sigs[i]))
         assert np.array_equal(rows_h[off_h[i]:off_h[i + 1]], want)
+
+
+@pytest.mark.parametrize("db", ["db", "db2"])
+def test_match_many_queries_per_cta(golden_match, db):
+    """More queries than persistent CTAs: every CTA reuses its scratch (dense
+    counters / histograms restored between queries) many times."""
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    qs = []
+    for rep in range(18):
+        for k in keys:
+            q = gm[k + "/q"].copy()
+            q[:, 0] += 3 * rep            # shifts every dtime, keeps the structure
+            qs.append(q[: len(q) - 7 * rep])
+    m = Matcher()
+    m.window, m.threshcount, m.search_depth = 2, 5, 100
+    got = m.match_batch(ht, qs)
+    assert len(got) == len(qs) == 432
+    for q, g in zip(qs, got):
+        w = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=2, threshcount=5, search_depth=100)
+        assert g.shape == w.shape and sorted(map(tuple, g)) == sorted(map(tuple, w))
+        assert np.array_equal(g[:, 1], w[:, 1])
