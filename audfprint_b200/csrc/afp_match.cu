@@ -21,7 +21,8 @@ namespace {
 
 constexpr int MT = 1024;          // threads per matching CTA (one CTA per SM, persistent over the queries)
 constexpr int NW = MT / 32;
-constexpr int ACAP = 1024;        // ids with raw > threshcount handled by the fast path
+constexpr int KCAP = 1024;        // candidate depth handled by the fast path (search_depth <= KCAP)
+constexpr int GCAP = 1024;        // radix select stops once the undecided set is this small
 constexpr int SLOT_SHIFT = 21;    // counter word = raw | (candidate slot + 1) << 21
 
 struct MatchArgs {
@@ -45,6 +46,10 @@ struct MatchArgs {
   int bias;
   int32_t* rows;    int row_cap;          // [nqueries][row_cap][7]
   int32_t* row_cnt;                       // [nqueries] rows produced (may exceed row_cap)
+  // sharded-table mode: publish every query's local top-sdepth candidate list
+  int publish;                            // 0/1
+  double* cand;                           // [nqueries][sdepth][3] = (id, raw, weight)
+  int32_t* cand_cnt;                      // [nqueries][2] = (entries, n_above)
 };
 
 // candidate order: (weighted count desc, id desc); keys are (bits of the positive double, id)
@@ -53,20 +58,40 @@ __device__ __forceinline__ bool key_gt(unsigned long long w1, unsigned i1, unsig
 }
 
 struct Shared {
-  unsigned long long a_w[ACAP];
-  unsigned a_id[ACAP];
-  unsigned a_raw[ACAP];
-  int a_rank[ACAP];      // bucket counts, then rank of A[j] among ALL distinct ids
-  int loff[ACAP];        // start of candidate j's dt list
-  int cur[ACAP];         // fill cursor of candidate j's dt list
-  unsigned char pass[ACAP];
+  unsigned long long a_w[KCAP + GCAP];   // gathered keys, sorted descending: the top-K' candidates
+  unsigned a_id[KCAP + GCAP];
+  unsigned a_raw[KCAP];
+  int loff[KCAP];        // start of candidate j's dt list
+  int cur[KCAP];         // fill cursor of candidate j's dt list
+  unsigned char pass[KCAP];
+  int rhist[256];        // radix-select digit histogram
   int wsum[NW];
   int val[NW], idx[NW];
   unsigned long long kw[NW];
   unsigned kid[NW];
-  unsigned nhits, ndist, nabove;
-  int dmin, dmax, nrows, ncand;
+  unsigned nhits, ndist, nabove, ngather;
+  int dmin, dmax, nrows;
+  int sel_digit, sel_need, sel_m;
 };
+
+// 96-bit composite key (weight bits, id), 12 digits of 8 bits from the top
+__device__ __forceinline__ unsigned key_digit(unsigned long long w, unsigned id, int p) {
+  return p < 8 ? (unsigned)(w >> (56 - 8 * p)) & 0xffu : (id >> (24 - 8 * (p - 8))) & 0xffu;
+}
+// compare the top `nfix` digits of (w,id) with those of the prefix: -1 below, 0 equal, +1 above
+__device__ __forceinline__ int prefix_cmp(unsigned long long w, unsigned id, unsigned long long pw, unsigned pid,
+                                          int nfix) {
+  if (nfix == 0) return 0;
+  if (nfix <= 8) {
+    const int sh = 64 - 8 * nfix;
+    const unsigned long long a = w >> sh, b = pw >> sh;
+    return a > b ? 1 : (a < b ? -1 : 0);
+  }
+  if (w != pw) return w > pw ? 1 : -1;
+  const int sh = 32 - 8 * (nfix - 8);
+  const unsigned a = sh ? id >> sh : id, b = sh ? pid >> sh : pid;
+  return a > b ? 1 : (a < b ? -1 : 0);
+}
 
 // inclusive scan of one int per thread over the CTA (MT threads)
 __device__ __forceinline__ int block_scan_incl(int v, int* wsum) {
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   for (int qi = blockIdx.x; qi < a.nqueries; qi += gridDim.x) {
     const int64_t q0 = a.qoff[qi];
     const int nq = (int)(a.qoff[qi + 1] - q0);
-    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; sh.ncand = 0; }
+    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; }
     __syncthreads();
     // ---- probe (hash_table.py:162-173): one warp per query row, every lane owns up to 4 slots;
     // all table loads and counter atomics of a row are in flight together
@@ -219,45 +244,96 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
     }
     __syncthreads();
     const int nhits = (int)sh.nhits, ndist = (int)sh.ndist;
-    // ---- weighted counts; ids above threshold go to A (audfprint_match.py:132-144)
-    for (int i0 = 0; i0 < ndist; i0 += MT) {
-      const int i = i0 + tid;
-      bool ab = false;
-      unsigned id = 0, raw = 0;
-      double w = 0.0;
-      if (i < ndist) {
-        id = dlist[i];
-        raw = __ldcg(cnt + id);
-        w = (double)raw / (double)a.hpi[id];
-        wtd[i] = w;
-        ab = raw > (uint32_t)a.thresh;
+    // ---- weighted counts, number of ids above threshold (audfprint_match.py:132-144)
+    {
+      unsigned above = 0;
+      for (int i = tid; i < ndist; i += MT) {
+        const unsigned id = dlist[i];
+        const unsigned raw = __ldcg(cnt + id);
+        wtd[i] = (double)raw / (double)a.hpi[id];
+        above += raw > (uint32_t)a.thresh ? 1u : 0u;
       }
-      const unsigned am = __ballot_sync(0xffffffffu, ab);
-      if (am) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&sh.nabove, (unsigned)__popc(am));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned pos = base + __popc(am & ((1u << lane) - 1u));
-        if (ab && pos < ACAP) {
-          sh.a_w[pos] = (unsigned long long)__double_as_longlong(w);
-          sh.a_id[pos] = id;
-          sh.a_raw[pos] = raw;
-        }
-      }
+      above = __reduce_add_sync(0xffffffffu, above);
+      if (lane == 0 && above) atomicAdd(&sh.nabove, above);
     }
     __syncthreads();
     const int nabove = (int)sh.nabove;
-    const int maxdepth = min(nabove, a.sdepth);
+    // candidate depth: min(#ids above threshold, search_depth) (:142-144); a table shard
+    // publishes its full local top-search_depth list instead (dist.merge_sharded_results)
+    const int maxdepth = a.publish ? min(ndist, a.sdepth) : min(nabove, a.sdepth);
     int32_t* qrows = a.rows + (size_t)qi * a.row_cap * 7;
 
-    if (maxdepth > 0 && nabove <= ACAP) {
-      // ---- fast path.  Only ids with raw > threshcount can produce rows, but their rank
-      // is their position among ALL distinct ids in (weight desc, id desc) order.
-      int n2 = 1;
-      while (n2 < nabove) n2 <<= 1;
-      for (int i = nabove + tid; i < n2; i += MT) { sh.a_w[i] = 0ull; sh.a_id[i] = 0u; sh.a_raw[i] = 0u; }
+    if (maxdepth > 0 && maxdepth <= KCAP) {
+      // ---- fast path: the top-`maxdepth` distinct ids by (weight desc, id desc) via an
+      // MSB-first radix select on the 96-bit key, stopped as soon as the undecided set fits
+      // in shared memory, then one small bitonic sort.  Position in the sorted list = rank.
+      unsigned long long pw = 0ull;
+      unsigned pid = 0u;
+      int nfix = 0, need = maxdepth, m = ndist;
+      while (m > GCAP && nfix < 12) {
+        for (int i = tid; i < 256; i += MT) sh.rhist[i] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < ndist; i0 += MT) {
+          const int i = i0 + tid;
+          int d = -1;
+          if (i < ndist) {
+            const unsigned long long w = (unsigned long long)__double_as_longlong(wtd[i]);
+            const unsigned id = dlist[i];
+            if (prefix_cmp(w, id, pw, pid, nfix) == 0) d = (int)key_digit(w, id, nfix);
+          }
+          const unsigned peers = __match_any_sync(0xffffffffu, d);   // warp-aggregated histogram
+          if (d >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sh.rhist[d], __popc(peers));
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int cum = 0, b = 255;
+          for (; b > 0; --b) {
+            if (cum + sh.rhist[b] >= need) break;
+            cum += sh.rhist[b];
+          }
+          sh.sel_digit = b;
+          sh.sel_need = need - cum;
+          sh.sel_m = sh.rhist[b];
+        }
+        __syncthreads();
+        const unsigned dg = (unsigned)sh.sel_digit;
+        if (nfix < 8) pw |= (unsigned long long)dg << (56 - 8 * nfix); else pid |= dg << (24 - 8 * (nfix - 8));
+        need = sh.sel_need;
+        m = sh.sel_m;
+        ++nfix;
+        __syncthreads();
+      }
+      if (tid == 0) sh.ngather = 0;
       __syncthreads();
-      for (int k = 2; k <= n2; k <<= 1)          // bitonic sort of A, descending
+      for (int i0 = 0; i0 < ndist; i0 += MT) {     // gather: decided-in ids + the undecided set
+        const int i = i0 + tid;
+        bool take = false;
+        unsigned long long w = 0ull;
+        unsigned id = 0u;
+        if (i < ndist) {
+          w = (unsigned long long)__double_as_longlong(wtd[i]);
+          id = dlist[i];
+          take = prefix_cmp(w, id, pw, pid, nfix) >= 0;
+        }
+        const unsigned tm = __ballot_sync(0xffffffffu, take);
+        if (tm) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&sh.ngather, (unsigned)__popc(tm));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (take) {
+            const unsigned pos = base + __popc(tm & ((1u << lane) - 1u));
+            sh.a_w[pos] = w;
+            sh.a_id[pos] = id;
+          }
+        }
+      }
+      __syncthreads();
+      const int ng = (int)sh.ngather;           // maxdepth <= ng <= maxdepth - need + m <= KCAP + GCAP
+      int n2 = 1;
+      while (n2 < ng) n2 <<= 1;
+      for (int i = ng + tid; i < n2; i += MT) { sh.a_w[i] = 0ull; sh.a_id[i] = 0u; }
+      __syncthreads();
+      for (int k = 2; k <= n2; k <<= 1)          // bitonic sort, descending
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int i = tid; i < n2; i += MT) {
             const int l = i ^ j;
@@ -267,47 +343,35 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
               if (gt != desc) {
                 const unsigned long long tw = sh.a_w[i]; sh.a_w[i] = sh.a_w[l]; sh.a_w[l] = tw;
                 const unsigned ti = sh.a_id[i]; sh.a_id[i] = sh.a_id[l]; sh.a_id[l] = ti;
-                const unsigned tr = sh.a_raw[i]; sh.a_raw[i] = sh.a_raw[l]; sh.a_raw[l] = tr;
               }
             }
           }
           __syncthreads();
         }
-      for (int i = tid; i < nabove; i += MT) sh.a_rank[i] = 0;
-      __syncthreads();
+      const int ncand = maxdepth;               // entries 0..maxdepth-1 of the sorted list, rank = index
       {
-        const unsigned long long wmin = sh.a_w[nabove - 1];
-        const unsigned idmin = sh.a_id[nabove - 1];
-        for (int i = tid; i < ndist; i += MT) {
-          const unsigned long long w = (unsigned long long)__double_as_longlong(wtd[i]);
-          if (w < wmin) continue;
-          const unsigned id = dlist[i];
-          if (!key_gt(w, id, wmin, idmin)) continue;
-          int lo = 0, hi = nabove;      // ge = #{j : A[j] >= key}; d outranks every A[j], j >= ge
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (!key_gt(w, id, sh.a_w[mid], sh.a_id[mid])) lo = mid + 1; else hi = mid;
+        unsigned raw = 0;
+        if (tid < ncand) {
+          raw = __ldcg(cnt + sh.a_id[tid]);
+          sh.a_raw[tid] = raw;
+          if (a.publish) {
+            double* c3 = a.cand + ((size_t)qi * a.sdepth + tid) * 3;
+            c3[0] = (double)sh.a_id[tid];
+            c3[1] = (double)raw;
+            c3[2] = __longlong_as_double((long long)sh.a_w[tid]);
           }
-          if (lo < nabove) atomicAdd(&sh.a_rank[lo], 1);
         }
-      }
-      __syncthreads();
-      {   // rank(A[j]) = inclusive prefix of the buckets; candidates are those with rank < maxdepth
-        const int b = (tid < nabove) ? sh.a_rank[tid] : 0;
-        const int rk = block_scan_incl(b, sh.wsum);
-        if (tid < nabove) sh.a_rank[tid] = rk;
-        const bool cand = tid < nabove && rk < maxdepth;
-        const int craw = cand ? (int)sh.a_raw[tid] : 0;
-        const int lend = block_scan_incl(craw, sh.wsum);       // ranks increase with j: candidates are a prefix
-        if (cand) {
-          sh.loff[tid] = lend - craw;
+        const bool rowable = tid < ncand && raw > (uint32_t)a.thresh;   // only these can yield rows (:291)
+        const int lraw = rowable ? (int)raw : 0;
+        const int lend = block_scan_incl(lraw, sh.wsum);
+        if (tid < ncand) {
+          sh.loff[tid] = lend - lraw;
           sh.cur[tid] = 0;
-          cnt[sh.a_id[tid]] = sh.a_raw[tid] | ((unsigned)(tid + 1) << SLOT_SHIFT);
-          atomicAdd(&sh.ncand, 1);
+          sh.pass[tid] = 0;
+          if (rowable) cnt[sh.a_id[tid]] = raw | ((unsigned)(tid + 1) << SLOT_SHIFT);
         }
       }
       __syncthreads();
-      const int ncand = sh.ncand;
       // ---- one pass over the hits: route the hits of candidates to their dt lists
       for (int i = tid; i < nhits; i += MT) {
         const uint2 h = hits[i];
@@ -319,6 +383,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
       // ---- quick filter, one warp per candidate: a row needs a dtime bin > threshcount (:291)
       for (int j = warp; j < ncand; j += NW) {
         const int n = (int)sh.a_raw[j];
+        if (n <= a.thresh) continue;       // warp-uniform
         const uint32_t* L = dts + sh.loff[j];
         int best = 0;
         for (int i = lane; i < n; i += 32) {
@@ -349,10 +414,10 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         dmax = __reduce_max_sync(0xffffffffu, dmax);
         if (lane == 0 && dmax >= 0) { atomicMin(&sh.dmin, dmin); atomicMax(&sh.dmax, dmax); }
         __syncthreads();
-        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, sh.a_id[j], n, sh.a_rank[j], qrows);
+        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, sh.a_id[j], n, j, qrows);
       }
     } else if (maxdepth > 0) {
-      // ---- slow path (more than ACAP ids above threshold): one pass over the distinct
+      // ---- slow path (search_depth > KCAP): one pass over the distinct
       // ids and one over the hits per candidate
       unsigned long long pw = ~0ull;
       unsigned pid = ~0u;
@@ -383,6 +448,10 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         if (!bvld) break;
         pw = bw; pid = bid; have_prev = true;
         const int raw = (int)(__ldcg(cnt + bid) & RAWMASK);
+        if (a.publish) {
+          double* c3 = a.cand + ((size_t)qi * a.sdepth + rank) * 3;
+          if (tid == 0) { c3[0] = (double)bid; c3[1] = (double)raw; c3[2] = __longlong_as_double((long long)bw); }
+        }
         if (raw <= a.thresh) continue;      // cannot yield a row (:291), but keeps its rank
         if (tid == 0) { sh.dmin = 0x7fffffff; sh.dmax = -1; }
         __syncthreads();
@@ -405,7 +474,13 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
     // ---- restore the counter array by replaying the distinct ids
     __syncthreads();
     for (int i = tid; i < ndist; i += MT) cnt[dlist[i]] = 0;
-    if (tid == 0) a.row_cnt[qi] = sh.nrows;
+    if (tid == 0) {
+      a.row_cnt[qi] = sh.nrows;
+      if (a.publish) {
+        a.cand_cnt[2 * qi] = maxdepth;
+        a.cand_cnt[2 * qi + 1] = nabove;
+      }
+    }
     __syncthreads();
   }
 }
@@ -682,6 +757,18 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   }
   a.rows = c->d_mrows.as<int32_t>();
   a.row_cnt = c->d_mrow_cnt.as<int32_t>();
+  a.publish = p->publish_candidates ? 1 : 0;
+  a.cand = nullptr;
+  a.cand_cnt = nullptr;
+  c->match_published = false;
+  if (a.publish) {
+    AFP_CUDA(c, c->d_mcand.reserve(sizeof(double) * 3 * (size_t)std::max(a.sdepth, 1) * (size_t)nqueries));
+    AFP_CUDA(c, c->d_mcand_cnt.reserve(sizeof(int32_t) * 2 * (size_t)nqueries));
+    a.cand = c->d_mcand.as<double>();
+    a.cand_cnt = c->d_mcand_cnt.as<int32_t>();
+    c->match_sdepth = a.sdepth;
+    c->match_published = true;
+  }
   c->match_row_cap = a.row_cap;
   afp_match_kernel<<<nctas, MT, 0, c->stream>>>(a);
   AFP_CUDA(c, cudaGetLastError());
@@ -711,6 +798,21 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   }
   c->match_total_rows = total;
   if (total_rows) *total_rows = total;
+  return AFP_OK;
+}
+
+int afp_fetch_match_candidates(afp_ctx* c, double* cand, int32_t* counts, int on_host) {
+  if (!c) return AFP_ERR_INVALID;
+  if (c->match_total_rows < 0 || !c->match_published)
+    AFP_FAIL(c, AFP_ERR_STATE, "afp_match_batch with publish_candidates has not been called");
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  const cudaMemcpyKind kind = on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (cand && c->match_nq > 0 && c->match_sdepth > 0)
+    AFP_CUDA(c, cudaMemcpyAsync(cand, c->d_mcand.p, sizeof(double) * 3 * (size_t)c->match_sdepth * (size_t)c->match_nq,
+                                kind, c->stream));
+  if (counts && c->match_nq > 0)
+    AFP_CUDA(c, cudaMemcpyAsync(counts, c->d_mcand_cnt.p, sizeof(int32_t) * 2 * (size_t)c->match_nq, kind, c->stream));
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
   return AFP_OK;
 }
 

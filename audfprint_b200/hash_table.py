@@ -264,7 +264,11 @@ class HashTable(object):
         """Upload table/counts/hashesperid if they changed since the last upload."""
         ctx = _lib.context(self.device)
         stamp = (id(self), self._version, id(self.table), id(self.counts))
+        shard = getattr(self, "_shard", None)
+        if shard is not None and ctx.table_key == ("shard", id(self), self._version, shard[0], shard[1]):
+            return ctx              # device copy is this table's shard
         if ctx.table_key != stamp:
+            self._shard = None
             table = np.ascontiguousarray(self.table, dtype=np.uint32)
             counts = np.ascontiguousarray(self.counts, dtype=np.int32)
             hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
@@ -272,6 +276,19 @@ class HashTable(object):
                                                int(self.depth), int(self.maxtimebits),
                                                hpi.ctypes.data if len(hpi) else None, len(hpi), 1))
             ctx.table_key = stamp
+        return ctx
+
+    def restrict_device_ids(self, id_lo, id_hi):
+        """Keep only entries of ids in [id_lo, id_hi) in the DEVICE copy (a table shard,
+        SURVEY.md §8e); the host arrays are untouched.  Any later mutation (or another
+        restrict) starts again from the full table."""
+        ctx = _lib.context(self.device)
+        ctx.table_key = None                      # force a fresh upload of the whole table
+        self._shard = None
+        ctx = self._sync_device()
+        ctx.check(ctx.lib.afp_table_restrict_ids(ctx.h, int(id_lo), int(id_hi)))
+        self._shard = (int(id_lo), int(id_hi))
+        ctx.table_key = ("shard", id(self), self._version, int(id_lo), int(id_hi))
         return ctx
 
     def get_hits(self, hashes):

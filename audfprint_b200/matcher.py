@@ -42,7 +42,7 @@ class Matcher(object):
             raise NotImplementedError("exact_count / find_time_range / illustrate are not implemented "
                                       "on the CUDA path (SURVEY.md §8f-4)")
         return _lib.MatcherParams(int(self.window), int(self.threshcount), int(self.search_depth),
-                                  int(self.max_alignments_per_id))
+                                  int(self.max_alignments_per_id), 0)
 
     def match_batch(self, ht, queries, sort=True):
         """Match many queries in one device call.
@@ -78,6 +78,34 @@ class Matcher(object):
                 r = r[(-r[:, 1]).argsort(), ]        # audfprint_match.py:335
             out.append(r)
         return out
+
+    def match_batch_shard(self, ht, queries):
+        """Table-shard side of a sharded match: `ht`'s device copy holds only
+        this rank's id range.  Returns one record per query for dist.merge_sharded_results:
+        {"n_above", "cand" (k,3) [id, raw, weight], "rows" (r,7) with LOCAL ranks}."""
+        arrs = [np.asarray(q, dtype=np.int32).reshape(-1, 2) for q in queries]
+        qoff = np.zeros(len(arrs) + 1, np.int64)
+        if arrs:
+            qoff[1:] = np.cumsum([len(a) for a in arrs])
+        packed = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros((0, 2), np.int32)
+        nq = len(arrs)
+        p = self._params()
+        p.publish_candidates = 1
+        ctx = ht._sync_device()
+        total = C.c_int64(0)
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
+                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
+        rows = np.empty((int(total.value), 7), np.int32)
+        roff = np.zeros(nq + 1, np.int64)
+        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        sd = max(int(self.search_depth), 1)
+        cand = np.zeros((nq, sd, 3), np.float64)
+        cnts = np.zeros((nq, 2), np.int32)
+        if nq:
+            ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        return [{"n_above": int(cnts[i, 1]), "cand": cand[i, :cnts[i, 0]].copy(),
+                 "rows": rows[roff[i]:roff[i + 1]].copy()} for i in range(nq)]
 
     def match_hashes(self, ht, hashes, hashesfor=None):
         """Query hashes -> rows (id, filteredmatches, timoffs, rawmatches, origrank,

@@ -71,6 +71,10 @@ typedef struct {
   int32_t threshcount;           /* Matcher.threshcount               */
   int32_t search_depth;          /* Matcher.search_depth              */
   int32_t max_alignments_per_id; /* Matcher.max_alignments_per_id     */
+  int32_t publish_candidates;    /* table-shard mode: 0 = off.  1 = rank and report
+                                  * the shard's full local top-search_depth ids of every query so
+                                  * that one all-gather + afp_fetch_match_candidates can rebuild
+                                  * the single-table result (audfprint_b200/dist.py)            */
 } afp_matcher_params;
 
 /* ---- context --------------------------------------------------------------- */
@@ -177,6 +181,10 @@ int afp_match_batch(afp_ctx* ctx, const int32_t* q_rows, int q_on_host, int32_t 
                     const int64_t* q_offsets, const afp_matcher_params* p,
                     int64_t* total_rows);
 int afp_fetch_match_rows(afp_ctx* ctx, int32_t* rows, int rows_on_host, int64_t* row_offsets);
+/* After afp_match_batch with publish_candidates = 1: `cand` float64
+ * [nqueries][search_depth][3] = (id, raw count, weighted count) in (weight desc, id desc)
+ * order, `counts` int32 [nqueries][2] = (entries used, #ids with raw > threshcount). */
+int afp_fetch_match_candidates(afp_ctx* ctx, double* cand, int32_t* counts, int on_host);
 
 #ifdef __cplusplus
 }

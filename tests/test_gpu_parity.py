@@ -237,3 +237,35 @@ def test_match_many_queries_per_cta(golden_match, db):
         w = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=2, threshcount=5, search_depth=100)
         assert g.shape == w.shape and sorted(map(tuple, g)) == sorted(map(tuple, w))
         assert np.array_equal(g[:, 1], w[:, 1])
+
+
+@pytest.mark.parametrize("db,nshards", [("db", 2), ("db2", 3)])
+def test_table_shards_publish_and_merge(golden_match, db, nshards):
+    """K4 in table-shard mode: restrict the device table to an id range, publish the local
+    top-search_depth candidates + rows, merge (dist.merge_sharded_results) == single table."""
+    from audfprint_b200 import dist as afd
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    qs = [gm[k + "/q"] for k in keys]
+    for cfg in ("a", "b"):
+        m = Matcher()
+        m.window, m.threshcount, m.search_depth = (int(x) for x in gm["cfg_" + cfg])
+        single = m.match_batch(ht, qs, sort=False)
+        per_shard = []
+        for s in range(nshards):
+            lo, hi = afd.id_range(len(hpi), s, nshards)
+            ht.restrict_device_ids(lo, hi)
+            recs = m.match_batch_shard(ht, qs)
+            # every published id is inside the shard, lists are sorted by (weight desc, id desc)
+            for r in recs:
+                c = r["cand"]
+                assert np.all((c[:, 0] >= lo) & (c[:, 0] < hi))
+                assert np.all((c[:-1, 2] > c[1:, 2]) | ((c[:-1, 2] == c[1:, 2]) & (c[:-1, 0] > c[1:, 0])))
+            per_shard.append(afd.unpack_shard_records(afd.pack_shard_records(recs, m.search_depth, 128), m.search_depth, 128))
+        ht._touch()                    # drop the shard: next call re-uploads the whole table
+        for qi in range(len(qs)):
+            merged = afd.merge_sharded_results([per_shard[s][qi] for s in range(nshards)], m.search_depth)
+            assert np.array_equal(merged, single[qi]), (db, cfg, keys[qi])
