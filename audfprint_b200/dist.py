@@ -168,3 +168,83 @@ def match_sharded(matcher, ht, queries, row_cap: int = 16, group=None):
         rows = merge_sharded_results([s[qi] for s in shards], matcher.search_depth)
         out.append(rows[(-rows[:, 1]).argsort(), ])          # audfprint_match.py:335
     return out
+
+
+# ---- vectorised form of the exchange for large query batches -------------------------
+def pack_shard_batch(cand, counts, rows, row_off, row_cap: int) -> np.ndarray:
+    """Same record layout as pack_shard_records, built without a Python loop from the arrays
+    afp_fetch_match_candidates / afp_fetch_match_rows return:
+    cand (nq, sd, 3) f64, counts (nq, 2) i32 [entries, n_above], rows (R, 7) i32, row_off (nq+1)."""
+    nq, sd = cand.shape[0], cand.shape[1]
+    nrows = np.diff(row_off)
+    if nq and nrows.max(initial=0) > row_cap:
+        raise ValueError("a shard produced %d rows for one query, row_cap is %d" % (int(nrows.max()), row_cap))
+    out = np.zeros((nq, 3 + 3 * sd + 7 * row_cap), np.float64)
+    out[:, 0] = counts[:, 1]
+    out[:, 1] = counts[:, 0]
+    out[:, 2] = nrows
+    valid = np.arange(sd)[None, :] < counts[:, :1]
+    out[:, 3:3 + 3 * sd] = np.where(valid[:, :, None], cand, 0.0).reshape(nq, 3 * sd)
+    if len(rows):
+        q = np.repeat(np.arange(nq), nrows)
+        k = np.arange(len(rows)) - np.repeat(row_off[:-1], nrows)
+        cols = 3 + 3 * sd + 7 * k[:, None] + np.arange(7)[None, :]
+        out[q[:, None], cols] = rows
+    return out
+
+
+def merge_shard_batch(gathered: np.ndarray, search_depth: int, row_cap: int):
+    """Vectorised merge_sharded_results over a whole batch.
+    gathered: (S, nq, W) packed records of all shards.  Returns (rows (R,7) int32 in
+    (query, global rank) order, row_off (nq+1))."""
+    S, nq, _ = gathered.shape
+    sd = max(int(search_depth), 1)
+    depth = np.minimum(gathered[:, :, 0].sum(axis=0), search_depth).astype(np.int64)        # (nq,)
+    ncand = gathered[:, :, 1].astype(np.int64)                                               # (S, nq)
+    cand = gathered[:, :, 3:3 + 3 * sd].reshape(S, nq, sd, 3)
+    valid = np.arange(sd)[None, None, :] < ncand[:, :, None]
+    ids = np.where(valid, cand[..., 0], -1.0).transpose(1, 0, 2).reshape(nq, S * sd)
+    wts = np.where(valid, cand[..., 2], -np.inf).transpose(1, 0, 2).reshape(nq, S * sd)
+    o1 = np.argsort(-ids, axis=1, kind="stable")                                             # id desc
+    o2 = np.argsort(-np.take_along_axis(wts, o1, axis=1), axis=1, kind="stable")              # weight desc
+    order = np.take_along_axis(o1, o2, axis=1)
+    sorted_ids = np.take_along_axis(ids, order, axis=1)                                      # (nq, S*sd)
+    nrows = gathered[:, :, 2].astype(np.int64)                                               # (S, nq)
+    rows = gathered[:, :, 3 + 3 * sd:].reshape(S, nq, row_cap, 7)
+    rvalid = np.arange(row_cap)[None, None, :] < nrows[:, :, None]
+    s_idx, q_idx, k_idx = np.nonzero(rvalid)
+    if len(q_idx) == 0:
+        return np.zeros((0, 7), np.int32), np.zeros(nq + 1, np.int64)
+    r = rows[s_idx, q_idx, k_idx].astype(np.int64)                                            # (R0, 7)
+    match = sorted_ids[q_idx] == r[:, :1]                                                     # (R0, S*sd)
+    pos = np.argmax(match, axis=1)
+    keep = match.any(axis=1) & (pos < depth[q_idx])
+    r, q_idx, pos, s_idx, k_idx = r[keep], q_idx[keep], pos[keep], s_idx[keep], k_idx[keep]
+    r[:, 4] = pos
+    o = np.lexsort((k_idx, pos, q_idx))            # query, then global rank, then emission order
+    r, q_idx = r[o], q_idx[o]
+    off = np.zeros(nq + 1, np.int64)
+    np.add.at(off, q_idx + 1, 1)
+    return r.astype(np.int32), np.cumsum(off)
+
+
+def match_sharded_batch(matcher, ht, packed_queries, row_cap: int = 16, group=None):
+    """Batch form of match_sharded: (query rows, offsets) in, (result rows, offsets) out, rows of
+    each query sorted by count descending (stable in global-rank order).  One all-gather."""
+    mine = matcher.match_batch_shard_packed(ht, packed_queries, row_cap)
+    rank, ws = world()
+    if ws == 1:
+        gathered = mine[None]
+    else:
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+            else torch.device("cpu")
+        t = torch.from_numpy(mine).to(dev)
+        out = torch.empty((ws * t.shape[0], t.shape[1]), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        gathered = out.cpu().numpy().reshape(ws, t.shape[0], t.shape[1])
+    rows, off = merge_shard_batch(gathered, matcher.search_depth, row_cap)
+    q = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    o = np.lexsort((np.arange(len(rows)), -rows[:, 1].astype(np.int64), q))
+    return rows[o], off

@@ -107,6 +107,31 @@ class Matcher(object):
         return [{"n_above": int(cnts[i, 1]), "cand": cand[i, :cnts[i, 0]].copy(),
                  "rows": rows[roff[i]:roff[i + 1]].copy()} for i in range(nq)]
 
+    def match_batch_shard_packed(self, ht, packed_queries, row_cap=16):
+        """match_batch_shard for a packed (rows, offsets) query batch, returning the fixed-size
+        float64 records (nq, W) that dist.allgather exchanges — no per-query Python work."""
+        from . import dist as afd
+        qrows, qoff = packed_queries
+        qrows = np.ascontiguousarray(qrows, dtype=np.int32).reshape(-1, 2)
+        qoff = np.ascontiguousarray(qoff, dtype=np.int64)
+        nq = len(qoff) - 1
+        p = self._params()
+        p.publish_candidates = 1
+        ctx = ht._sync_device()
+        total = C.c_int64(0)
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, qrows.ctypes.data if len(qrows) else None, 1, nq,
+                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
+        rows = np.empty((int(total.value), 7), np.int32)
+        roff = np.zeros(nq + 1, np.int64)
+        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        sd = max(int(self.search_depth), 1)
+        cand = np.zeros((nq, sd, 3), np.float64)
+        cnts = np.zeros((nq, 2), np.int32)
+        if nq:
+            ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        return afd.pack_shard_batch(cand, cnts, rows, roff, row_cap)
+
     def match_hashes(self, ht, hashes, hashesfor=None):
         """Query hashes -> rows (id, filteredmatches, timoffs, rawmatches, origrank,
         mintime, maxtime), best first (audfprint_match.py:314-352)."""

@@ -269,3 +269,23 @@ def test_table_shards_publish_and_merge(golden_match, db, nshards):
         for qi in range(len(qs)):
             merged = afd.merge_sharded_results([per_shard[s][qi] for s in range(nshards)], m.search_depth)
             assert np.array_equal(merged, single[qi]), (db, cfg, keys[qi])
+
+
+def test_shard_batch_path_single_rank(golden_match):
+    """world_size 1: match_sharded_batch (packed records, vectorised merge) == match_batch."""
+    from audfprint_b200 import dist as afd
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, "db2")
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    qs = [gm[k + "/q"] for k in keys]
+    qoff = np.zeros(len(qs) + 1, np.int64)
+    qoff[1:] = np.cumsum([len(q) for q in qs])
+    m = Matcher()
+    m.window, m.threshcount, m.search_depth = 2, 5, 100
+    rows, off = afd.match_sharded_batch(m, ht, (np.concatenate(qs), qoff), row_cap=64)
+    single = m.match_batch(ht, qs, sort=False)
+    for i, s in enumerate(single):
+        want = s[np.argsort(-s[:, 1], kind="stable")]
+        assert np.array_equal(rows[off[i]:off[i + 1]], want)
