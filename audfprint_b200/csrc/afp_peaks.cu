@@ -9,8 +9,9 @@
 //   peak list build (column-major, bins ascending)     :303-308
 //
 // The time recursion is strictly sequential inside an item, so the unit of
-// parallelism is ONE WARP PER ITEM: lane l owns bins 8l..8l+7 (threshold, filter
-// state and the current column live in registers), neighbour compares use warp
+// parallelism is ONE WARP PER ITEM (one warp per CTA): lane l owns bins
+// 8l..8l+7 (threshold, filter state and the current column live in registers), the column stream arrives through a TMA bulk-copy ring in shared
+// memory (3 chunks of 4 columns in flight per warp), neighbour compares use warp
 // shuffles, the per-column top-N selection uses redux.sync (warp-wide integer
 // max on the bit pattern of the positive doubles), and thousands of items run
 // concurrently.  All arithmetic that feeds a comparison is done with explicit
@@ -22,6 +23,9 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int CH = 4;      // columns per TMA chunk (8 KB)
+constexpr int NST = 3;     // chunks in flight per warp (24 KB ring)
+constexpr int PFB = 8;     // prefetch distance (columns) of the backward pass
 
 struct PeakArgs {
   const ItemDesc* items;
@@ -40,7 +44,17 @@ struct PeakArgs {
   int32_t* item_npeaks;
 };
 
+// Lane l owns the 8 contiguous bins 8l..8l+7 (register j = bin & 7): the local-max test
+// then needs only one neighbour exchange per side.  The Gaussian table is stored with one
+// pad element per 8 (index k + k/8) so that the lanes' 64-byte-strided reads hit distinct banks.
+__device__ __forceinline__ int bin_of(int lane, int j) { return 8 * lane + j; }
+__device__ __forceinline__ int lane_of(int pos) { return pos >> 3; }
+__device__ __forceinline__ int reg_of(int pos) { return pos & 7; }
 __device__ __forceinline__ int gidx(int k) { return k + (k >> 3); }   // padded table index
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 
 // thr = max(thr, val * E[bin - pos]) for the 8 bins of this lane
 // (audfprint_analyze.py:225-227 / :193-196)
@@ -87,23 +101,10 @@ __device__ __forceinline__ void spread(const double (&v)[8], double (&thr)[8], c
       const int j = __ffs(mm) - 1;
       mm &= mm - 1;
       const double val = __shfl_sync(FULL, pick(v, j), src);
-      bump(thr, sE, lane, 8 * src + j, val);
+      bump(thr, sE, lane, bin_of(src, j), val);
     }
   }
 }
-
-struct ColLoader {
-  const double2* p;
-  __device__ __forceinline__ void load(int64_t col, int lane, double (&x)[8]) const {
-    const double2* q = p + col * (AFP_NBINS / 2) + lane * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double2 v = __ldg(q + j);
-      x[2 * j] = v.x;
-      x[2 * j + 1] = v.y;
-    }
-  }
-};
 
 // floor, mean removal and one step of the DF2T high-pass
 // y = z + x ; z = -x + pole*y   (scipy lfilter order)
@@ -118,14 +119,64 @@ __device__ __forceinline__ void hpf_step(const double (&l)[8], double (&z)[8], d
   }
 }
 
-constexpr int PF = 4;   // prefetch distance (columns) of the forward / backward loops
+// The column stream of one item: chunks of CH columns are TMA-bulk-copied into a ring of
+// NST shared-memory stages (one mbarrier each), NST chunks ahead of the consumer.
+struct ColRing {
+  double* buf;                 // NST * CH * 256 doubles
+  unsigned long long* bar;     // NST mbarriers
+  const double* src;           // column 0 of the item
+  int T;
+  int lane;
+
+  __device__ __forceinline__ void issue(int chunk) const {   // lane 0 only
+    const int c0 = chunk * CH;
+    const uint32_t bytes = (uint32_t)min(CH, T - c0) * AFP_NBINS * sizeof(double);
+    unsigned long long* b = bar + (chunk % NST);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(buf + (chunk % NST) * CH * AFP_NBINS)),
+                 "l"(src + (size_t)c0 * AFP_NBINS), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+  }
+  __device__ __forceinline__ void wait(int chunk) const {
+    const uint32_t parity = (chunk / NST) & 1;
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(bar + (chunk % NST))), "r"(parity)
+          : "memory");
+    }
+  }
+  // read column t; with `consume`, the chunk is recycled after its last column
+  __device__ __forceinline__ void load(int t, double (&x)[8], bool consume) const {
+    const int chunk = t / CH;
+    if (t % CH == 0 || !consume) wait(chunk);
+    const double2* p = reinterpret_cast<const double2*>(buf + ((chunk % NST) * CH + t % CH) * AFP_NBINS) + 4 * lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 v = p[i];
+      x[2 * i] = v.x;
+      x[2 * i + 1] = v.y;
+    }
+    if (consume && (t % CH == CH - 1 || t == T - 1)) {
+      __syncwarp();
+      if (lane == 0 && (chunk + NST) * CH < T) issue(chunk + NST);
+    }
+  }
+};
 
 __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
-  __shared__ double sE[AFP_GAUSS_PAD];
+  __shared__ __align__(16) double sE[AFP_GAUSS_PAD];
+  __shared__ __align__(128) double sCol[NST * CH * AFP_NBINS];
+  __shared__ unsigned long long sBar[NST];
   const int lane = threadIdx.x;
   const int item = a.item0 + blockIdx.x;
   for (int k = lane; k < AFP_GAUSS_N; k += 32) sE[gidx(k)] = a.gauss[k];
-  __syncwarp();
 
   const ItemDesc it = a.items[item];
   const ItemStats st = a.stats[item];
@@ -141,22 +192,27 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     }
     return;
   }
+  ColRing ring{sCol, sBar, a.logs + base * AFP_NBINS, T, lane};
+  if (lane == 0) {
+    for (int i = 0; i < NST; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(sBar + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < NST && c * CH < T; ++c) ring.issue(c);
+  }
+  __syncwarp();
   const double lf = st.logfloor, mean = st.mean, pole = a.pole, a_dec = a.a_dec;
-  ColLoader ld{reinterpret_cast<const double2*>(a.logs) + base * (AFP_NBINS / 2)};
 
-  double thr[8], z[8], s[8], sn[8];
-  double lb[PF][8];   // register ring of prefetched columns (memory latency >> one column step)
+  double thr[8], z[8], s[8], sn[8], l[8];
 
   // ---- initial threshold: spread of the per-bin max over the first 10 columns
-  // (audfprint_analyze.py:204-206)
+  // (audfprint_analyze.py:204-206); the ring holds columns 0..11, nothing is consumed yet
   {
     double mx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { z[j] = 0.0; mx[j] = -INFINITY; }
     const int n0 = min(10, T);
     for (int t = 0; t < n0; ++t) {
-      ld.load(t, lane, lb[0]);
-      hpf_step(lb[0], z, s, lf, mean, pole);
+      ring.load(t, l, false);
+      hpf_step(l, z, s, lf, mean, pole);
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = fmax(mx[j], s[j]);
     }
@@ -168,63 +224,54 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
   // the threshold) before the threshold-dependent decisions of column t.
 #pragma unroll
   for (int j = 0; j < 8; ++j) z[j] = 0.0;
-#pragma unroll
-  for (int u = 0; u < PF; ++u)
-    if (u < T) ld.load(u, lane, lb[u]);
-  hpf_step(lb[0], z, s, lf, mean, pole);
+  ring.load(0, l, true);
+  hpf_step(l, z, s, lf, mean, pole);
   unsigned lm = locmax_mask(s, lane);
-  if (PF < T) ld.load(PF, lane, lb[0]);
-  for (int t0 = 0; t0 < T; t0 += PF) {
+  for (int t = 0; t < T; ++t) {
+    unsigned lmn = 0;
+    if (t + 1 < T) {
+      ring.load(t + 1, l, true);
+      hpf_step(l, z, sn, lf, mean, pole);
+      lmn = locmax_mask(sn, lane);
+    }
+    unsigned cmask = lm;
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int t = t0 + u;
-      if (t < T) {   // warp-uniform
-        unsigned lmn = 0;
-        if (t + 1 < T) {
-          hpf_step(lb[(u + 1) % PF], z, sn, lf, mean, pole);
-          lmn = locmax_mask(sn, lane);
-          if (t + 1 + PF < T) ld.load(t + 1 + PF, lane, lb[(u + 1) % PF]);
+    for (int j = 0; j < 8; ++j) cmask &= (s[j] > thr[j]) ? ~0u : ~(1u << j);
+    int npk = 0;
+    if (__ballot_sync(FULL, cmask != 0)) {
+      // accept candidates by (value desc, bin desc) (:220), at most maxpks (:221)
+      while (true) {
+        unsigned long long bk = 0ull;
+        int bj = -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // bins ascend with j inside a lane: >= keeps the higher bin on ties
+          const unsigned long long k = (unsigned long long)__double_as_longlong(s[j]);
+          if (((cmask >> j) & 1u) && k >= bk) { bk = k; bj = j; }
         }
-        unsigned cmask = lm;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cmask &= (s[j] > thr[j]) ? ~0u : ~(1u << j);
-        int npk = 0;
-        if (__ballot_sync(FULL, cmask != 0)) {
-          // accept candidates by (value desc, bin desc) (:220), at most maxpks (:221)
-          while (true) {
-            unsigned long long bk = 0ull;
-            int bj = -1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const unsigned long long k = (unsigned long long)__double_as_longlong(s[j]);
-              if (((cmask >> j) & 1u) && k >= bk) { bk = k; bj = j; }
-            }
-            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
-            const unsigned mhi = __reduce_max_sync(FULL, bj >= 0 ? hi : 0u);
-            const bool v1 = bj >= 0 && hi == mhi;
-            const unsigned mlo = __reduce_max_sync(FULL, v1 ? lo : 0u);
-            const bool v2 = v1 && lo == mlo;
-            const int pos = (int)__reduce_max_sync(FULL, v2 ? (unsigned)(8 * lane + bj + 1) : 0u) - 1;
-            const double val = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-            if (lane == (pos >> 3)) cmask &= ~(1u << (pos & 7));
-            bump(thr, sE, lane, pos, val);
-            if (lane == 0) {
-              a.fwd_val[(base + t) * maxpks + npk] = val;
-              a.fwd_bin[(base + t) * maxpks + npk] = (uint8_t)pos;
-            }
-            ++npk;
-            if (npk >= maxpks || !__ballot_sync(FULL, cmask != 0)) break;
-          }
+        const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+        const unsigned mhi = __reduce_max_sync(FULL, bj >= 0 ? hi : 0u);
+        const bool v1 = bj >= 0 && hi == mhi;
+        const unsigned mlo = __reduce_max_sync(FULL, v1 ? lo : 0u);
+        const bool v2 = v1 && lo == mlo;
+        const int pos = (int)__reduce_max_sync(FULL, v2 ? (unsigned)(bin_of(lane, bj) + 1) : 0u) - 1;
+        const double val = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        if (lane == lane_of(pos)) cmask &= ~(1u << reg_of(pos));
+        bump(thr, sE, lane, pos, val);
+        if (lane == 0) {
+          a.fwd_val[(base + t) * maxpks + npk] = val;
+          a.fwd_bin[(base + t) * maxpks + npk] = (uint8_t)pos;
         }
-        if (lane == 0) a.fwd_cnt[base + t] = (uint8_t)npk;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(thr[j], a_dec);
-        if (t + 1 < T) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s[j] = sn[j];
-          lm = lmn;
-        }
+        ++npk;
+        if (npk >= maxpks || !__ballot_sync(FULL, cmask != 0)) break;
       }
+    }
+    if (lane == 0) a.fwd_cnt[base + t] = (uint8_t)npk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) thr[j] = __dmul_rn(thr[j], a_dec);
+    if (t + 1 < T) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = sn[j];
+      lm = lmn;
     }
   }
   __syncwarp();   // make lane 0's fwd_* stores visible to the whole warp
@@ -251,8 +298,8 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     npeaks += c;
   };
   // prefetch ring over columns T-1, T-2, ...: count + this lane's slot (if lane < maxpks)
-  int pc[PF], pb[PF];
-  double pv[PF];
+  int pc[PFB], pb[PFB];
+  double pv[PFB];
   const bool slot = lane < maxpks;
   auto fetch = [&](int t, int& c, double& v, int& b) {
     c = a.fwd_cnt[base + t];
@@ -260,23 +307,23 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     b = slot ? (int)a.fwd_bin[(base + t) * maxpks + lane] : -1;
   };
 #pragma unroll
-  for (int u = 0; u < PF; ++u)
+  for (int u = 0; u < PFB; ++u)
     if (T - 1 - u >= 0) fetch(T - 1 - u, pc[u], pv[u], pb[u]);
-  for (int t0 = T - 1; t0 >= 0; t0 -= PF) {
+  for (int t0 = T - 1; t0 >= 0; t0 -= PFB) {
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
+    for (int u = 0; u < PFB; ++u) {
       const int t = t0 - u;
       if (t >= 0) {   // warp-uniform
         const int n = pc[u];
         const double my_val = pv[u];
         const int my_bin = (lane < n) ? pb[u] : -1;
-        if (t - PF >= 0) fetch(t - PF, pc[u], pv[u], pb[u]);
+        if (t - PFB >= 0) fetch(t - PFB, pc[u], pv[u], pb[u]);
         int cur_alive = 0;
         for (int k = 0; k < n; ++k) {   // stored order is already (value desc, bin desc) (:241)
           const double val = __shfl_sync(FULL, my_val, k);
           const int pos = __shfl_sync(FULL, my_bin, k);
-          const bool ok = val >= pick(thr, pos & 7);
-          if ((__ballot_sync(FULL, ok) >> (pos >> 3)) & 1u) {   // :242, decided by the owning lane
+          const bool ok = val >= pick(thr, reg_of(pos));
+          if ((__ballot_sync(FULL, ok) >> lane_of(pos)) & 1u) {   // :242, decided by the owning lane
             bump(thr, sE, lane, pos, val);                     // :244-245
             if (lane == k) cur_alive = 1;
             if (nxt_alive && nxt_bin == pos) nxt_alive = 0;    // :247-248 same bin, following column
