@@ -23,7 +23,10 @@ constexpr int MT = 1024;          // threads per matching CTA (one CTA per SM, p
 constexpr int NW = MT / 32;
 constexpr int KCAP = 1024;        // candidate depth handled by the fast path (search_depth <= KCAP)
 constexpr int GCAP = 1024;        // radix select stops once the undecided set is this small
-constexpr int SLOT_SHIFT = 21;    // counter word = raw | (candidate slot + 1) << 21
+constexpr int QCAP = 4096;        // query rows sorted in shared memory to merge probes of one bucket
+constexpr int SLOT_SHIFT = 21;    // per-query hit capacity (rows * depth) stays below 2^21
+constexpr int HSET_BITS = 11;     // candidate hash set: 2048 entries for <= KCAP = 1024 keys
+constexpr int HSET = 1 << HSET_BITS;
 
 struct MatchArgs {
   const int32_t* q;        // [sum nq][2]
@@ -189,6 +192,7 @@ __device__ void candidate_modes(const MatchArgs& a, Shared& sh, int32_t* hist, i
 
 __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   __shared__ Shared sh;
+  extern __shared__ unsigned long long s_q[];   // QCAP (bucket << 32 | query time) keys
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint2* hits = a.hits + (size_t)blockIdx.x * a.hits_cap;
   uint32_t* dlist = a.dlist + (size_t)blockIdx.x * a.hits_cap;
@@ -205,11 +209,44 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
     const int nq = (int)(a.qoff[qi + 1] - q0);
     if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; }
     __syncthreads();
-    // ---- probe (hash_table.py:162-173): one warp per query row, every lane owns up to 4 slots;
-    // all table loads and counter atomics of a row are in flight together
+    // ---- probe (hash_table.py:162-173).  A query made of several sub-frame shifts probes
+    // the same bucket up to `shifts` times (same hash at neighbouring times): the rows are
+    // sorted by bucket in shared memory so that every distinct bucket is read ONCE and every
+    // (bucket, id) pair costs ONE counter atomic of weight m.  Hit order is irrelevant
+    // downstream (raw counts and dtime histograms are order-free).
+    const bool sorted = nq <= QCAP;
+    int n2 = 1;
+    if (sorted) {
+      while (n2 < nq) n2 <<= 1;
+      for (int i = tid; i < n2; i += MT)
+        s_q[i] = i < nq ? ((unsigned long long)((uint32_t)a.q[2 * (q0 + i) + 1] & hmask) << 32) |
+                              (uint32_t)a.q[2 * (q0 + i)]
+                        : ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= n2; k <<= 1)          // bitonic sort, ascending (bucket, time)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < n2; i += MT) {
+            const int l = i ^ j;
+            if (l > i) {
+              const unsigned long long x = s_q[i], y = s_q[l];
+              if ((x > y) == ((i & k) == 0)) { s_q[i] = y; s_q[l] = x; }
+            }
+          }
+          __syncthreads();
+        }
+    }
     for (int r = warp; r < nq; r += NW) {
-      const int qt = a.q[2 * (q0 + r)];
-      const uint32_t b = (uint32_t)a.q[2 * (q0 + r) + 1] & hmask;
+      uint32_t b;
+      int m = 1, qt0 = 0;
+      if (sorted) {
+        const unsigned long long e = s_q[r];
+        b = (uint32_t)(e >> 32);
+        if (r > 0 && (uint32_t)(s_q[r - 1] >> 32) == b) continue;      // not the head of its bucket group
+        while (r + m < nq && (uint32_t)(s_q[r + m] >> 32) == b) ++m;
+      } else {
+        qt0 = a.q[2 * (q0 + r)];
+        b = (uint32_t)a.q[2 * (q0 + r) + 1] & hmask;
+      }
       const int n = min(a.depth, a.counts[b]);
       const uint32_t* row = a.table + (size_t)b * a.depth;
       for (int s0 = 0; s0 < n; s0 += 128) {
@@ -218,15 +255,19 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         for (int u = 0; u < 4; ++u) v[u] = (s0 + 32 * u + lane < n) ? row[s0 + 32 * u + lane] : 0u;
         const int chunk = min(128, n - s0);
         unsigned basepos = 0;
-        if (lane == 0) basepos = atomicAdd(&sh.nhits, (unsigned)chunk);
+        if (lane == 0) basepos = atomicAdd(&sh.nhits, (unsigned)(chunk * m));
         basepos = __shfl_sync(0xffffffffu, basepos, 0);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           old[u] = 1u;
           if (s0 + 32 * u + lane < n) {
             const uint32_t id = (v[u] >> a.mtb) - 1u;
-            hits[basepos + 32 * u + lane] = make_uint2(id, (unsigned)((int)(v[u] & tmask) - qt + a.bias));
-            if (id < (uint32_t)a.nids) old[u] = atomicAdd(&cnt[id], 1u);
+            const int rt = (int)(v[u] & tmask) + a.bias;
+            for (int k = 0; k < m; ++k) {
+              const int qt = sorted ? (int)(uint32_t)s_q[r + k] : qt0;
+              hits[basepos + k * chunk + 32 * u + lane] = make_uint2(id, (unsigned)(rt - qt));
+            }
+            if (id < (uint32_t)a.nids) old[u] = atomicAdd(&cnt[id], (unsigned)m);
           }
         }
 #pragma unroll
@@ -368,16 +409,35 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
           sh.loff[tid] = lend - lraw;
           sh.cur[tid] = 0;
           sh.pass[tid] = 0;
-          if (rowable) cnt[sh.a_id[tid]] = raw | ((unsigned)(tid + 1) << SLOT_SHIFT);
         }
-      }
-      __syncthreads();
-      // ---- one pass over the hits: route the hits of candidates to their dt lists
-      for (int i = tid; i < nhits; i += MT) {
-        const uint2 h = hits[i];
-        if (h.x >= (uint32_t)a.nids) continue;
-        const unsigned c = __ldcg(cnt + h.x) >> SLOT_SHIFT;
-        if (c) dts[sh.loff[c - 1] + atomicAdd(&sh.cur[c - 1], 1)] = h.y;
+        // id -> candidate slot: open-addressing hash set in the (now free) upper halves of the
+        // sort arrays, so that routing the hits costs no global access
+        unsigned* hkey = reinterpret_cast<unsigned*>(sh.a_w + KCAP);              // HSET entries
+        unsigned short* hval = reinterpret_cast<unsigned short*>(sh.a_id + KCAP);
+        for (int i = tid; i < HSET; i += MT) hkey[i] = 0u;
+        __syncthreads();
+        if (rowable) {
+          const unsigned key = sh.a_id[tid] + 1u;
+          unsigned h = (sh.a_id[tid] * 2654435761u) >> (32 - HSET_BITS);
+          while (atomicCAS(&hkey[h], 0u, key) != 0u) h = (h + 1u) & (HSET - 1);
+          hval[h] = (unsigned short)tid;
+        }
+        __syncthreads();
+        // ---- one pass over the hits: route the hits of candidates to their dt lists
+        for (int i = tid; i < nhits; i += MT) {
+          const uint2 hh = hits[i];
+          const unsigned key = hh.x + 1u;
+          unsigned h = (hh.x * 2654435761u) >> (32 - HSET_BITS);
+          unsigned k;
+          while ((k = hkey[h]) != 0u) {
+            if (k == key) {
+              const int slot = hval[h];
+              dts[sh.loff[slot] + atomicAdd(&sh.cur[slot], 1)] = hh.y;
+              break;
+            }
+            h = (h + 1u) & (HSET - 1);
+          }
+        }
       }
       __syncthreads();
       // ---- quick filter, one warp per candidate: a row needs a dtime bin > threshcount (:291)
@@ -770,7 +830,9 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
     c->match_published = true;
   }
   c->match_row_cap = a.row_cap;
-  afp_match_kernel<<<nctas, MT, 0, c->stream>>>(a);
+  AFP_CUDA(c, cudaFuncSetAttribute(afp_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(QCAP * sizeof(unsigned long long))));
+  afp_match_kernel<<<nctas, MT, QCAP * sizeof(unsigned long long), c->stream>>>(a);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
   // clamp counts to the capacity (flagging overflow), scan, pack

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
 
     const bool active = g < cur.nft;
     const int64_t frame = cur.frame0 + g;
-    double vmax = 0.0, vmin = INFINITY, vsum = 0.0;
+    double vmax = 0.0, vsum = 0.0;
+    int hmin = 0x7ff00000;   // min over the high words of 4|X|^2 (positive doubles order like their bits)
     double zr[16], zi[16];
     if (active) {
       // step A: z[16q + r] = (x[2n] w[2n], x[2n+1] w[2n+1]), n = 16q + r
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
             a.mag[frame * 257 + 256 - k] = sqrt(0.25 * ssb);
           }
           vmax = fmax(vmax, fmax(ssa, ssb));
-          vmin = fmin(vmin, fmin(la, lb));
+          hmin = min(hmin, min(__double2hiint(ssa), __double2hiint(ssb)));
           vsum += la + lb;
         }
       }
@@ -322,15 +323,21 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
         out[128] = lg;
         if (WRITE_MAG) a.mag[frame * 257 + 128] = sqrt(0.25 * ss);
         vmax = fmax(vmax, ss);
-        vmin = fmin(vmin, lg);
+        hmin = min(hmin, __double2hiint(ss));
         vsum += lg;
       }
     }
     // deterministic CTA reduction of (max |S|^2, min log, sum log)
+    // a LOWER bound of the smallest log: the high word alone (low word zeroed).  The
+    // statistics pass only asks "is anything below the floor?"; a false alarm just takes its
+    // exact path.
+    hmin = __reduce_min_sync(0xffffffffu, hmin);
+    const double v_lo = __hiloint2double(hmin, 0);
+    double vmin = hmin >= 0x7ff00000 ? INFINITY      // this warp had no frame in the tile
+                  : (hmin < 0x00100000 ? -INFINITY : half_log_quarter(v_lo, s_logtab));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
       vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
     }
     if (lane == 0) {
