@@ -198,10 +198,24 @@ class Analyzer(object):
             rows = rows[:int(total.value)]
         return rows, roff
 
+    # frames of log-spectrogram workspace per device call (2 KB each): 8 M frames = 16 GB
+    max_frames_per_call = 8 << 20
+
     def fingerprint_batch(self, signals, shifts=None):
-        """List of 1-D signals (int16 or float) -> list of int32 (U,2) hash arrays."""
+        """List of 1-D signals (int16 or float) -> list of int32 (U,2) hash arrays.
+        Long lists are cut into device calls of at most `max_frames_per_call` frames."""
         if len(signals) == 0:
             return []
+        nsh = max(1, int(self.shifts if shifts is None else shifts))
+        frames = [nsh * (1 + len(x) // self.n_hop) for x in signals]
+        if sum(frames) > self.max_frames_per_call and len(signals) > 1:
+            out, start, acc = [], 0, 0
+            for i, f in enumerate(frames):
+                if acc + f > self.max_frames_per_call and i > start:
+                    out += self.fingerprint_batch(signals[start:i], shifts)
+                    start, acc = i, 0
+                acc += f
+            return out + self.fingerprint_batch(signals[start:], shifts)
         arrs = [_as_pcm(s) for s in signals]
         kinds = set(k for _, k in arrs)
         if len(kinds) > 1:

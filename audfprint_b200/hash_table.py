@@ -46,6 +46,29 @@ class _RefUnpickler(pickle.Unpickler):
         return super().find_class(module, name)
 
 
+_REF_ATTRS = ("hashbits", "depth", "maxtimebits", "table", "counts", "names", "hashesperid", "params",
+              "ht_version", "dirty")
+
+
+def _as_reference_object(ht):
+    """An object that pickles as `hash_table.HashTable` with the reference's attribute set.
+    If the reference module is not importable a stand-in module of that name is registered
+    for the duration of the dump (pickle stores only the class PATH, not its code)."""
+    import sys
+    import types
+    mod = sys.modules.get("hash_table")
+    cls = getattr(mod, "HashTable", None) if mod is not None else None
+    if cls is None:
+        mod = types.ModuleType("hash_table")
+        cls = type("HashTable", (object,), {"__module__": "hash_table"})
+        mod.HashTable = cls
+        sys.modules["hash_table"] = mod
+    obj = object.__new__(cls)
+    obj.__dict__.update({k: getattr(ht, k) for k in _REF_ATTRS})
+    obj.__dict__["dirty"] = False
+    return obj
+
+
 class HashTable(object):
     """Fixed-array hash table of (id, time) entries keyed by landmark hash."""
 
@@ -209,11 +232,14 @@ class HashTable(object):
 
     # ---- persistence (gzip pickle, hash_table.py:178-246) -------------------------------
     def save(self, name, params=None, file_object=None):
+        """gzip pickle in the REFERENCE's on-disk format (hash_table.py:178-190): the
+        stream names the class `hash_table.HashTable` and carries exactly its attributes,
+        so the reference loads files written here and vice versa."""
         if params:
             for key in params:
                 self.params[key] = params[key]
         f = file_object if file_object else gzip.open(name, 'wb')
-        pickle.dump(self, f, pickle.HIGHEST_PROTOCOL)
+        pickle.dump(_as_reference_object(self), f, pickle.HIGHEST_PROTOCOL)
         if not file_object:
             f.close()
         self.dirty = False

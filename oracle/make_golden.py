@@ -153,6 +153,17 @@ def main():
                       m[key + "/truth"][1] // 256, "ties", tie_w, tie_c)
     np.savez_compressed(os.path.join(OUT, "match.npz"), **m)
 
+    # a small database saved by the reference's own HashTable.save (gzip pickle of the object,
+    # hash_table.py:178-197): the mirror class must load it (tests/test_abi_cpu.py)
+    random.seed(99)
+    small = ref_ht.HashTable(hashbits=10, depth=4, maxtime=1 << 10)
+    for i in range(6):
+        small.store("ref_track%d" % i, track_hashes[i][:120])
+    small.params["samplerate"] = 11025
+    small.save(os.path.join(OUT, "ref_db.pklz"))
+    np.savez_compressed(os.path.join(OUT, "ref_db_arrays.npz"), table=small.table, counts=small.counts,
+                        hashesperid=np.asarray(small.hashesperid))
+
 
 if __name__ == "__main__":
     main()
