@@ -23,7 +23,8 @@ constexpr int MT = 1024;          // threads per matching CTA (one CTA per SM, p
 constexpr int NW = MT / 32;
 constexpr int KCAP = 1024;        // candidate depth handled by the fast path (search_depth <= KCAP)
 constexpr int GCAP = 1024;        // radix select stops once the undecided set is this small
-constexpr int QCAP = 4096;        // query rows sorted in shared memory to merge probes of one bucket
+constexpr int QCAP = 16384;       // query rows sorted in shared memory to merge probes of one bucket (128 KB)
+constexpr int CSEG = 32768;       // track ids counted per pass in shared memory (u32 counters, the same 128 KB)
 constexpr int SLOT_SHIFT = 21;    // per-query hit capacity (rows * depth) stays below 2^21
 constexpr int HSET_BITS = 11;     // candidate hash set: 2048 entries for <= KCAP = 1024 keys
 constexpr int HSET = 1 << HSET_BITS;
@@ -43,7 +44,8 @@ struct MatchArgs {
   uint32_t* dlist;                        // distinct ids, hits_cap
   double* wtd;                            // weighted count per dlist entry, hits_cap
   uint32_t* dts;                          // dt + bias of the candidates' hits, grouped per candidate, hits_cap
-  uint32_t* counters;                     // nids
+  uint32_t* recs;                         // (id << 8 | weight) of every distinct (bucket, slot), hits_cap
+  uint32_t* rawl;                         // raw count per dlist entry, hits_cap
   int32_t* hist;    int hist_len;         // dtime histogram
   int32_t* filt;                          // local-max filtered copy
   int bias;
@@ -72,9 +74,11 @@ struct Shared {
   int val[NW], idx[NW];
   unsigned long long kw[NW];
   unsigned kid[NW];
-  unsigned nhits, ndist, nabove, ngather;
+  unsigned nhits, ndist, nabove, ngather, nrec;
   int dmin, dmax, nrows;
   int sel_digit, sel_need, sel_m;
+  int segoff[514];       // record range of every id segment (nids < 2^24 -> <= 512 segments)
+  int segcur[512];
 };
 
 // 96-bit composite key (weight bits, id), 12 digits of 8 bits from the top
@@ -190,6 +194,17 @@ __device__ void candidate_modes(const MatchArgs& a, Shared& sh, int32_t* hist, i
   __syncthreads();
 }
 
+// raw count of a selected id from its weight: w = raw / hpi correctly rounded, so
+// rint(w * hpi) == raw exactly (raw < 2^21).  hashesperid == 0 (w = inf) falls back to a scan.
+__device__ __forceinline__ unsigned raw_of(const MatchArgs& a, unsigned long long wbits, unsigned id,
+                                           const uint32_t* dlist, const uint32_t* rawl, int ndist) {
+  const unsigned h = a.hpi[id];
+  if (h != 0u) return __double2uint_rn(__longlong_as_double((long long)wbits) * (double)h);
+  for (int i = 0; i < ndist; ++i)
+    if (dlist[i] == id) return rawl[i];
+  return 0u;
+}
+
 __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   __shared__ Shared sh;
   extern __shared__ unsigned long long s_q[];   // QCAP (bucket << 32 | query time) keys
@@ -198,16 +213,17 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   uint32_t* dlist = a.dlist + (size_t)blockIdx.x * a.hits_cap;
   double* wtd = a.wtd + (size_t)blockIdx.x * a.hits_cap;
   uint32_t* dts = a.dts + (size_t)blockIdx.x * a.hits_cap;
-  uint32_t* cnt = a.counters + (size_t)blockIdx.x * a.nids;
+  uint32_t* recs = a.recs + (size_t)blockIdx.x * a.hits_cap;
+  uint32_t* rawl = a.rawl + (size_t)blockIdx.x * a.hits_cap;
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_q);   // CSEG counters, aliases the sorted query rows
   int32_t* hist = a.hist + (size_t)blockIdx.x * a.hist_len;
   int32_t* filt = a.filt + (size_t)blockIdx.x * a.hist_len;
   const uint32_t hmask = (1u << a.hashbits) - 1u, tmask = (1u << a.mtb) - 1u;
-  const uint32_t RAWMASK = (1u << SLOT_SHIFT) - 1u;
 
   for (int qi = blockIdx.x; qi < a.nqueries; qi += gridDim.x) {
     const int64_t q0 = a.qoff[qi];
     const int nq = (int)(a.qoff[qi + 1] - q0);
-    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; }
+    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; sh.nrec = 0; }
     __syncthreads();
     // ---- probe (hash_table.py:162-173).  A query made of several sub-frame shifts probes
     // the same bucket up to `shifts` times (same hash at neighbouring times): the rows are
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
       const int n = min(a.depth, a.counts[b]);
       const uint32_t* row = a.table + (size_t)b * a.depth;
       for (int s0 = 0; s0 < n; s0 += 128) {
-        uint32_t v[4], old[4];
+        uint32_t v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = (s0 + 32 * u + lane < n) ? row[s0 + 32 * u + lane] : 0u;
         const int chunk = min(128, n - s0);
@@ -259,45 +275,105 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         basepos = __shfl_sync(0xffffffffu, basepos, 0);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          old[u] = 1u;
+          bool rec = false;
+          uint32_t id = 0;
           if (s0 + 32 * u + lane < n) {
-            const uint32_t id = (v[u] >> a.mtb) - 1u;
+            id = (v[u] >> a.mtb) - 1u;
             const int rt = (int)(v[u] & tmask) + a.bias;
             for (int k = 0; k < m; ++k) {
               const int qt = sorted ? (int)(uint32_t)s_q[r + k] : qt0;
               hits[basepos + k * chunk + 32 * u + lane] = make_uint2(id, (unsigned)(rt - qt));
             }
-            if (id < (uint32_t)a.nids) old[u] = atomicAdd(&cnt[id], (unsigned)m);
+            rec = id < (uint32_t)a.nids;
           }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {   // first touch of an id -> distinct list (warp-aggregated append)
-          const bool first = old[u] == 0u;
-          const unsigned fm = __ballot_sync(0xffffffffu, first);
-          if (fm) {
+          // one record (id, weight m) per distinct (bucket, slot): the raw counts are built
+          // from these in shared memory, no global atomics
+          const unsigned rm = __ballot_sync(0xffffffffu, rec);
+          const int per = (m + 254) / 255;                       // weights above 255 are split
+          if (rm) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&sh.ndist, (unsigned)__popc(fm));
+            if (lane == 0) base = atomicAdd(&sh.nrec, (unsigned)(__popc(rm) * per));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (first) dlist[base + __popc(fm & ((1u << lane) - 1u))] = (v[u] >> a.mtb) - 1u;
+            if (rec) {
+              uint32_t* dst = recs + base + __popc(rm & ((1u << lane) - 1u)) * per;
+              for (int k = 0, left = m; k < per; ++k, left -= 255) dst[k] = (id << 8) | (uint32_t)min(left, 255);
+            }
           }
         }
       }
     }
     __syncthreads();
-    const int nhits = (int)sh.nhits, ndist = (int)sh.ndist;
-    // ---- weighted counts, number of ids above threshold (audfprint_match.py:132-144)
+    // ---- raw count per track and weighted counts (audfprint_match.py:129-144): the ids are
+    // swept in segments of CSEG, each counted in shared memory (the 128 KB that held the
+    // sorted query rows), then every non-zero counter becomes a distinct-list entry
     {
+      const int nrec = (int)sh.nrec;
+      const int nseg = (int)((a.nids + CSEG - 1) / CSEG);        // <= 512 (nids < 2^24)
+      // group the records by id segment (counting sort: histogram, scan, scatter into `dts`)
+      // so that each counting pass reads only its own records instead of all of them
+      for (int i = tid; i <= nseg; i += MT) sh.segoff[i] = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < nrec; i0 += 4 * MT) {
+        uint32_t rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rr[u] = (i0 + u * MT + tid < nrec) ? recs[i0 + u * MT + tid] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rr[u] != 0xffffffffu) atomicAdd(&sh.segoff[(rr[u] >> 8) / CSEG + 1], 1);
+      }
+      __syncthreads();
+      if (tid == 0)
+        for (int i = 1; i <= nseg; ++i) sh.segoff[i] += sh.segoff[i - 1];
+      __syncthreads();
+      for (int i = tid; i < nseg; i += MT) sh.segcur[i] = sh.segoff[i];
+      __syncthreads();
+      for (int i0 = 0; i0 < nrec; i0 += 4 * MT) {
+        uint32_t rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rr[u] = (i0 + u * MT + tid < nrec) ? recs[i0 + u * MT + tid] : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rr[u] != 0xffffffffu) dts[atomicAdd(&sh.segcur[(rr[u] >> 8) / CSEG], 1)] = rr[u];
+      }
+      __syncthreads();
       unsigned above = 0;
-      for (int i = tid; i < ndist; i += MT) {
-        const unsigned id = dlist[i];
-        const unsigned raw = __ldcg(cnt + id);
-        wtd[i] = (double)raw / (double)a.hpi[id];
-        above += raw > (uint32_t)a.thresh ? 1u : 0u;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int r0 = sh.segoff[sg], r1 = sh.segoff[sg + 1];
+        if (r1 == r0) continue;                                   // uniform: no id of this segment was hit
+        const uint32_t seg0 = (uint32_t)sg * CSEG;
+        uint4* z4 = reinterpret_cast<uint4*>(s_cnt);
+        for (int i = tid; i < CSEG / 4; i += MT) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        for (int i = r0 + tid; i < r1; i += MT) {
+          const uint32_t rr = dts[i];
+          atomicAdd(&s_cnt[(rr >> 8) - seg0], rr & 255u);
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < CSEG; j0 += MT) {
+          const unsigned raw = s_cnt[j0 + tid];
+          const unsigned hm = __ballot_sync(0xffffffffu, raw != 0u);
+          if (hm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&sh.ndist, (unsigned)__popc(hm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (raw) {
+              const unsigned pos = base + __popc(hm & ((1u << lane) - 1u));
+              const unsigned id = seg0 + j0 + tid;
+              dlist[pos] = id;
+              rawl[pos] = raw;
+              wtd[pos] = (double)raw / (double)a.hpi[id];
+              above += raw > (uint32_t)a.thresh ? 1u : 0u;
+            }
+          }
+        }
+        __syncthreads();
       }
       above = __reduce_add_sync(0xffffffffu, above);
       if (lane == 0 && above) atomicAdd(&sh.nabove, above);
     }
     __syncthreads();
+    __syncthreads();
+    const int nhits = (int)sh.nhits, ndist = (int)sh.ndist;
     const int nabove = (int)sh.nabove;
     // candidate depth: min(#ids above threshold, search_depth) (:142-144); a table shard
     // publishes its full local top-search_depth list instead (dist.merge_sharded_results)
@@ -314,16 +390,23 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
       while (m > GCAP && nfix < 12) {
         for (int i = tid; i < 256; i += MT) sh.rhist[i] = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < ndist; i0 += MT) {
-          const int i = i0 + tid;
-          int d = -1;
-          if (i < ndist) {
-            const unsigned long long w = (unsigned long long)__double_as_longlong(wtd[i]);
-            const unsigned id = dlist[i];
-            if (prefix_cmp(w, id, pw, pid, nfix) == 0) d = (int)key_digit(w, id, nfix);
+        for (int i0 = 0; i0 < ndist; i0 += 4 * MT) {
+          unsigned long long w4[4];
+          unsigned id4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * MT + tid;
+            w4[u] = i < ndist ? (unsigned long long)__double_as_longlong(wtd[i]) : 0ull;
+            id4[u] = i < ndist ? dlist[i] : 0u;
           }
-          const unsigned peers = __match_any_sync(0xffffffffu, d);   // warp-aggregated histogram
-          if (d >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sh.rhist[d], __popc(peers));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int d = -1;
+            if (i0 + u * MT + tid < ndist && prefix_cmp(w4[u], id4[u], pw, pid, nfix) == 0)
+              d = (int)key_digit(w4[u], id4[u], nfix);
+            const unsigned peers = __match_any_sync(0xffffffffu, d);   // warp-aggregated histogram
+            if (d >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sh.rhist[d], __popc(peers));
+          }
         }
         __syncthreads();
         if (tid == 0) {
@@ -393,7 +476,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
       {
         unsigned raw = 0;
         if (tid < ncand) {
-          raw = __ldcg(cnt + sh.a_id[tid]);
+          raw = raw_of(a, sh.a_w[tid], sh.a_id[tid], dlist, rawl, ndist);
           sh.a_raw[tid] = raw;
           if (a.publish) {
             double* c3 = a.cand + ((size_t)qi * a.sdepth + tid) * 3;
@@ -424,8 +507,15 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         }
         __syncthreads();
         // ---- one pass over the hits: route the hits of candidates to their dt lists
-        for (int i = tid; i < nhits; i += MT) {
-          const uint2 hh = hits[i];
+        for (int i0 = 0; i0 < nhits; i0 += 4 * MT) {
+          uint2 h4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            h4[u] = (i0 + u * MT + tid < nhits) ? hits[i0 + u * MT + tid] : make_uint2(0xffffffffu, 0u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+          const uint2 hh = h4[u];
+          if (hh.x == 0xffffffffu) continue;
           const unsigned key = hh.x + 1u;
           unsigned h = (hh.x * 2654435761u) >> (32 - HSET_BITS);
           unsigned k;
@@ -436,6 +526,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
               break;
             }
             h = (h + 1u) & (HSET - 1);
+          }
           }
         }
       }
@@ -507,7 +598,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
           if (sh.val[w] && (!bvld || key_gt(sh.kw[w], sh.kid[w], bw, bid))) { bw = sh.kw[w]; bid = sh.kid[w]; bvld = true; }
         if (!bvld) break;
         pw = bw; pid = bid; have_prev = true;
-        const int raw = (int)(__ldcg(cnt + bid) & RAWMASK);
+        const int raw = (int)raw_of(a, bw, bid, dlist, rawl, ndist);
         if (a.publish) {
           double* c3 = a.cand + ((size_t)qi * a.sdepth + rank) * 3;
           if (tid == 0) { c3[0] = (double)bid; c3[1] = (double)raw; c3[2] = __longlong_as_double((long long)bw); }
@@ -531,9 +622,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, bid, raw, rank, qrows);
       }
     }
-    // ---- restore the counter array by replaying the distinct ids
     __syncthreads();
-    for (int i = tid; i < ndist; i += MT) cnt[dlist[i]] = 0;
     if (tid == 0) {
       a.row_cnt[qi] = sh.nrows;
       if (a.publish) {
@@ -785,10 +874,10 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.row_cap = 256;
   const char* env = getenv("AFP_MATCH_ROW_CAP");
   if (env && atoi(env) > 0) a.row_cap = atoi(env);
-  if (a.hits_cap >= ((int64_t)1 << SLOT_SHIFT))
-    AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large: rows * depth must stay below 2^21");
-  const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + 2 * sizeof(uint32_t) + sizeof(double)) +
-                         (size_t)a.nids * sizeof(uint32_t) + (size_t)a.hist_len * 2 * sizeof(int32_t) + 256;
+  if (a.hits_cap >= ((int64_t)1 << SLOT_SHIFT) || a.nids >= ((int64_t)1 << 24))
+    AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large (rows * depth >= 2^21) or more than 2^24 track ids");
+  const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + 4 * sizeof(uint32_t) + sizeof(double)) +
+                         (size_t)a.hist_len * 2 * sizeof(int32_t) + 256;
   const size_t before = c->d_mscratch.cap;
   AFP_CUDA(c, c->d_mscratch.reserve(per_cta * (size_t)nctas + 1024));
   AFP_CUDA(c, c->d_mrows.reserve(sizeof(int32_t) * 7 * (size_t)a.row_cap * (size_t)nqueries));
@@ -803,8 +892,9 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.wtd = (double*)carve(sizeof(double) * a.hits_cap * nctas);
   a.dlist = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
   a.dts = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
+  a.recs = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
+  a.rawl = (uint32_t*)carve(sizeof(uint32_t) * a.hits_cap * nctas);
   char* zero0 = base;
-  a.counters = (uint32_t*)carve(sizeof(uint32_t) * (size_t)a.nids * nctas);
   a.hist = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
   a.filt = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
   // counters and histograms are left zeroed by the kernel itself: clear them only when the
