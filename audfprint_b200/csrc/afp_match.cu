@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   int32_t* hist = a.hist + (size_t)blockIdx.x * a.hist_len;
   int32_t* filt = a.filt + (size_t)blockIdx.x * a.hist_len;
   const uint32_t hmask = (1u << a.hashbits) - 1u, tmask = (1u << a.mtb) - 1u;
+  for (int i = tid; i < CSEG / 4; i += MT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
 
   for (int qi = blockIdx.x; qi < a.nqueries; qi += gridDim.x) {
     const int64_t q0 = a.qoff[qi];
@@ -336,21 +338,33 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
           if (rr[u] != 0xffffffffu) dts[atomicAdd(&sh.segcur[(rr[u] >> 8) / CSEG], 1)] = rr[u];
       }
       __syncthreads();
+      // the counters must start from zero: clear what the sorted query rows occupied (every
+      // pass below leaves the array zeroed again)
+      {
+        uint4* z4 = reinterpret_cast<uint4*>(s_cnt);
+        const int nz = sorted ? n2 / 2 : 0;                      // n2 keys of 8 bytes = n2/2 uint4
+        for (int i = tid; i < nz; i += MT) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      __syncthreads();
       unsigned above = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const int r0 = sh.segoff[sg], r1 = sh.segoff[sg + 1];
         if (r1 == r0) continue;                                   // uniform: no id of this segment was hit
         const uint32_t seg0 = (uint32_t)sg * CSEG;
-        uint4* z4 = reinterpret_cast<uint4*>(s_cnt);
-        for (int i = tid; i < CSEG / 4; i += MT) z4[i] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
         for (int i = r0 + tid; i < r1; i += MT) {
           const uint32_t rr = dts[i];
           atomicAdd(&s_cnt[(rr >> 8) - seg0], rr & 255u);
         }
         __syncthreads();
-        for (int j0 = 0; j0 < CSEG; j0 += MT) {
-          const unsigned raw = s_cnt[j0 + tid];
+        // harvest through the records again: whoever swaps a non-zero counter out owns that id;
+        // the array is all-zero afterwards (no scan of 32768 counters, no re-zeroing)
+        for (int i0 = r0; i0 < r1; i0 += MT) {
+          const int i = i0 + tid;
+          unsigned raw = 0, id = 0;
+          if (i < r1) {
+            id = dts[i] >> 8;
+            raw = atomicExch(&s_cnt[id - seg0], 0u);
+          }
           const unsigned hm = __ballot_sync(0xffffffffu, raw != 0u);
           if (hm) {
             unsigned base = 0;
@@ -358,7 +372,6 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
             base = __shfl_sync(0xffffffffu, base, 0);
             if (raw) {
               const unsigned pos = base + __popc(hm & ((1u << lane) - 1u));
-              const unsigned id = seg0 + j0 + tid;
               dlist[pos] = id;
               rawl[pos] = raw;
               wtd[pos] = (double)raw / (double)a.hpi[id];
