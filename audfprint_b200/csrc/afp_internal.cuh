@@ -49,7 +49,7 @@ struct ItemStats {
   double logfloor;   // log(max|S| / 1e6)
   double mean;       // mean of the floored log-magnitudes over 257 x T
   int32_t allzero;   // 1 when max|S| == 0 (reference skips log/mean, audfprint_analyze.py:287-290)
-  int32_t pad;
+  int32_t floored;   // 1 while the tile sums of this item still have to be recomputed with the floor
 };
 
 struct TableDev {

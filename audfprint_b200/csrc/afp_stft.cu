@@ -380,60 +380,73 @@ constexpr size_t k1_smem_bytes(size_t pcm_elem, int nbuf) {
 }
 
 // ---- per-item statistics: floor, mean (audfprint_analyze.py:283-286) ----------
-// One CTA per item.  Fast path: no value below the floor -> mean from the tile
-// partial sums (fixed order, deterministic).  Slow path (digital silence etc.):
-// re-read the stored logs and sum max(L, floor).
-__global__ void __launch_bounds__(256) afp_stats_kernel(const ItemDesc* items, int item0,
-                                                        const double* tile_stats, const double* logs,
-                                                        const double* nyq, ItemStats* out) {
-  __shared__ double s_a[256], s_b[256], s_c[256];
-  const int item = item0 + blockIdx.x;
+// Three tiny launches.  (1) one WARP per item reduces the tile partials in a fixed order
+// (deterministic): floor, all-zero flag, mean of the un-floored logs, and whether anything
+// may sit below the floor.  (2) For such items only (digital silence, or the rare file whose
+// smallest bin is 120 dB below its largest) the tile sums are recomputed with the floor
+// applied, one CTA per tile so that a single long file cannot serialise the batch.
+// (3) the means of those items are re-reduced.
+__global__ void __launch_bounds__(256) afp_stats_kernel(const ItemDesc* items, int item0, int nitems,
+                                                        const double* tile_stats, ItemStats* out, int phase) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nitems) return;
+  const int item = item0 + w;
+  if (phase == 1 && !out[item].floored) return;       // only items whose tile sums were floored
   const ItemDesc it = items[item];
-  const int tid = threadIdx.x;
   const int ntiles = (it.nframes + FT - 1) / FT;
   double m = 0.0, mn = INFINITY, sm = 0.0;
-  for (int i = tid; i < ntiles; i += 256) {
+  for (int i = lane; i < ntiles; i += 32) {
     const double* ts = tile_stats + (size_t)(it.tile_base + i) * 3;
     m = fmax(m, ts[0]);
     mn = fmin(mn, ts[1]);
     sm += ts[2];
   }
-  s_a[tid] = m; s_b[tid] = mn; s_c[tid] = sm;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      s_a[tid] = fmax(s_a[tid], s_a[tid + o]);
-      s_b[tid] = fmin(s_b[tid], s_b[tid + o]);
-      s_c[tid] += s_c[tid + o];
-    }
-    __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
   }
-  const double maxss = s_a[0], minlog = s_b[0];
-  double total = s_c[0];
-  __syncthreads();
-  const bool allzero = !(maxss > 0.0);
-  const double logfloor = allzero ? 0.0 : log(sqrt(maxss) / 1e6);
-  if (!allzero && minlog < logfloor) {   // uniform across the CTA
-    const size_t nl = (size_t)it.nframes * AFP_NBINS;
-    const double* L = logs + (size_t)it.frame_base * AFP_NBINS;
-    double acc = 0.0;
-    for (size_t i = tid; i < nl; i += 256) acc += fmax(L[i], logfloor);
-    for (int i = tid; i < it.nframes; i += 256) acc += fmax(nyq[it.frame_base + i], logfloor);
-    s_c[tid] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) s_c[tid] += s_c[tid + o];
-      __syncthreads();
-    }
-    total = s_c[0];
-  }
-  if (tid == 0) {
+  if (lane == 0) {
+    const bool allzero = !(m > 0.0);
     ItemStats st;
-    st.logfloor = logfloor;
-    st.mean = (allzero || it.nframes == 0) ? 0.0 : total / ((double)it.nframes * 257.0);
+    st.logfloor = allzero ? 0.0 : log(sqrt(m) / 1e6);
+    st.mean = (allzero || it.nframes == 0) ? 0.0 : sm / ((double)it.nframes * 257.0);
     st.allzero = allzero ? 1 : 0;
-    st.pad = 0;
+    st.floored = (phase == 0 && !allzero && mn < st.logfloor) ? 1 : 0;   // needs the floored sums
     out[item] = st;
+  }
+}
+
+// floored tile sums of the flagged items: grid (items, FS_SPLIT); un-flagged items leave after
+// one load, a flagged item's tiles are dealt round-robin to its FS_SPLIT CTAs
+constexpr int FS_SPLIT = 8;
+__global__ void __launch_bounds__(256) afp_floorsum_kernel(const ItemDesc* items, int item0, const ItemStats* stats,
+                                                           const double* logs, const double* nyq,
+                                                           double* tile_stats) {
+  __shared__ double s_part[8];
+  const int item = item0 + blockIdx.x;
+  const ItemStats st = stats[item];
+  if (!st.floored) return;                        // uniform
+  const ItemDesc it = items[item];
+  const int ntiles = (it.nframes + FT - 1) / FT;
+  for (int k = blockIdx.y; k < ntiles; k += FS_SPLIT) {
+    const int t0 = k * FT, nft = min(FT, it.nframes - t0);
+    const double* L = logs + (size_t)(it.frame_base + t0) * AFP_NBINS;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nft * AFP_NBINS; i += 256) acc += fmax(L[i], st.logfloor);
+    if ((int)threadIdx.x < nft) acc += fmax(nyq[it.frame_base + t0 + threadIdx.x], st.logfloor);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s_part[w];
+      tile_stats[(size_t)(it.tile_base + k) * 3 + 2] = t;
+    }
   }
 }
 
@@ -508,11 +521,17 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
 
 int afp_launch_stats(afp_ctx* c, int item0, int nitems) {
   if (nitems <= 0) return AFP_OK;
-  afp_stats_kernel<<<nitems, 256, 0, c->stream>>>(c->d_items.as<ItemDesc>(), item0,
-                                                     c->d_tile_stats.as<double>(), c->d_logs.as<double>(),
-                                                     c->d_nyq.as<double>(), c->d_item_stats.as<ItemStats>());
+  const ItemDesc* items = c->d_items.as<ItemDesc>();
+  ItemStats* st = c->d_item_stats.as<ItemStats>();
+  double* ts = c->d_tile_stats.as<double>();
+  afp_stats_kernel<<<(nitems + 7) / 8, 256, 0, c->stream>>>(items, item0, nitems, ts, st, 0);
   AFP_CUDA(c, cudaGetLastError());
-  c->launches++;
+  afp_floorsum_kernel<<<dim3((unsigned)nitems, FS_SPLIT), 256, 0, c->stream>>>(items, item0, st, c->d_logs.as<double>(),
+                                                                            c->d_nyq.as<double>(), ts);
+  AFP_CUDA(c, cudaGetLastError());
+  afp_stats_kernel<<<(nitems + 7) / 8, 256, 0, c->stream>>>(items, item0, nitems, ts, st, 1);
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches += 3;
   return AFP_OK;
 }
 
