@@ -121,7 +121,7 @@ struct afp_ctx {
   TableDev tab;
   DevBuf d_q, d_qoff, d_hit_off, d_hits;
   int64_t nhits = -1, hits_nq = 0;
-  DevBuf d_mscratch, d_mcounters, d_mrows, d_mrow_cnt, d_mrow_off, d_mrows_packed, d_mcand, d_mcand_cnt;
+  DevBuf d_mscratch, d_mrows, d_mrow_cnt, d_mrow_off, d_mrows_packed, d_mcand, d_mcand_cnt;
   int32_t match_sdepth = 0;
   bool match_published = false;
   int32_t match_nq = 0;

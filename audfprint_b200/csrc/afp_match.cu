@@ -5,11 +5,11 @@
 // Matcher._best_count_ids (audfprint_match.py:124-147) and
 // Matcher._approx_match_counts (:241-312, find_time_range off).
 //
-// One CTA per query (persistent over the batch).  Each CTA owns a private
-// scratch region in HBM (L2-resident in practice): the hit list, a dense
-// per-track counter array that is cleared by replaying the list of distinct ids
-// (never memset), and a dense dtime histogram cleared over the touched range.
-// The results do not depend on hit order, so hits are appended with atomics.
+// One 1024-thread CTA per query (persistent over the batch, one per SM).  Each CTA
+// owns a private scratch region in HBM (hit list, records, distinct-id list, dense
+// dtime histogram cleared over the touched range); the per-track raw counts are
+// built in shared memory, segment by segment.  Results do not depend on hit
+// order, so hits and records are appended with (shared-memory) atomics.
 //
 // Tie rule (documented deviation, see oracle/afp_oracle.py::rank_candidates):
 // the reference reverses an unstable argsort, so the order of equal weighted
@@ -894,7 +894,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   const size_t before = c->d_mscratch.cap;
   AFP_CUDA(c, c->d_mscratch.reserve(per_cta * (size_t)nctas + 1024));
   AFP_CUDA(c, c->d_mrows.reserve(sizeof(int32_t) * 7 * (size_t)a.row_cap * (size_t)nqueries));
-  // carve the scratch; counters and histograms must start (and are left) zeroed
+  // carve the scratch; the histograms must start (and are left) zeroed
   char* base = c->d_mscratch.as<char>();
   auto carve = [&](size_t bytes) {
     char* p0 = base;
@@ -910,7 +910,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   char* zero0 = base;
   a.hist = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
   a.filt = (int32_t*)carve(sizeof(int32_t) * (size_t)a.hist_len * nctas);
-  // counters and histograms are left zeroed by the kernel itself: clear them only when the
+  // the histograms are left zeroed by the kernel itself: clear them only when the
   // carve-up changed (or the buffer moved)
   const uint64_t layout = (uint64_t)a.hits_cap * 1000003ull ^ (uint64_t)a.nids * 7919ull ^ (uint64_t)a.hist_len * 31ull ^
                           (uint64_t)(uintptr_t)c->d_mscratch.p ^ (uint64_t)before;

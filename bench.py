@@ -358,6 +358,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
+    if a.impl != "reference":
+        cores = max(2, cores // max(1, world))      # every rank forks its own generator pool
     nsamp = int(round(a.seconds * SR))
     config = {"workload": "batch fingerprint %d x %g s synthetic 11025 Hz mono int16 files per GPU "
                           "(BASELINE configs[1])" % (a.files, a.seconds),
