@@ -20,6 +20,10 @@ class AfpError(RuntimeError):
     pass
 
 
+class RowCapacityError(AfpError):
+    """afp_match_batch: a query produced more rows than row_capacity (retry with more)."""
+
+
 class AnalyzerParams(C.Structure):
     _fields_ = [("a_dec", C.c_double), ("hpf_pole", C.c_double), ("maxpksperframe", C.c_int32),
                 ("maxpairsperpeak", C.c_int32), ("targetdf", C.c_int32), ("mindt", C.c_int32),
@@ -28,7 +32,8 @@ class AnalyzerParams(C.Structure):
 
 class MatcherParams(C.Structure):
     _fields_ = [("window", C.c_int32), ("threshcount", C.c_int32), ("search_depth", C.c_int32),
-                ("max_alignments_per_id", C.c_int32), ("publish_candidates", C.c_int32)]
+                ("max_alignments_per_id", C.c_int32), ("publish_candidates", C.c_int32),
+                ("row_capacity", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -131,6 +136,8 @@ class Context:
             msg = msg.decode() if msg else ""
             if rc == -2:
                 raise ValueError("libafp: " + msg)
+            if rc == -3 and msg.startswith("row capacity exceeded"):
+                raise RowCapacityError(msg)
             raise AfpError("libafp status %d: %s" % (rc, msg))
 
     def set_stream(self, cuda_stream: int | None):

@@ -884,9 +884,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.hits_cap = std::max<int64_t>(maxnq * c->tab.depth, 1);
   a.bias = h_mm[0] + p->window + 2;
   a.hist_len = (1 << c->tab.maxtimebits) + a.bias + p->window + 4;
-  a.row_cap = 256;
-  const char* env = getenv("AFP_MATCH_ROW_CAP");
-  if (env && atoi(env) > 0) a.row_cap = atoi(env);
+  a.row_cap = p->row_capacity > 0 ? p->row_capacity : 256;
   if (a.hits_cap >= ((int64_t)1 << SLOT_SHIFT) || a.nids >= ((int64_t)1 << 24))
     AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large (rows * depth >= 2^21) or more than 2^24 track ids");
   const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + 4 * sizeof(uint32_t) + sizeof(double)) +
@@ -953,7 +951,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
                               cudaMemcpyDeviceToHost, c->stream));
   AFP_CUDA(c, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (over) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "a query produced more rows than AFP_MATCH_ROW_CAP (default 256)");
+  if (over) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "row capacity exceeded: a query produced more rows than afp_matcher_params.row_capacity");
   AFP_CUDA(c, c->d_mrows_packed.reserve(sizeof(int32_t) * 7 * (size_t)(total + 1)));
   if (total > 0) {
     afp_pack_rows_kernel<<<nqueries, 64, 0, c->stream>>>(a.rows, a.row_cnt, c->d_mrow_off.as<int64_t>(), a.row_cap,

@@ -42,7 +42,26 @@ class Matcher(object):
             raise NotImplementedError("exact_count / find_time_range / illustrate are not implemented "
                                       "on the CUDA path (SURVEY.md §8f-4)")
         return _lib.MatcherParams(int(self.window), int(self.threshcount), int(self.search_depth),
-                                  int(self.max_alignments_per_id), 0)
+                                  int(self.max_alignments_per_id), 0, 0)
+
+    @staticmethod
+    def _run(ctx, p, packed, nq, qoff):
+        """afp_match_batch, growing the per-query row capacity when a query overflows it."""
+        total = C.c_int64(0)
+        cap = 256
+        while True:
+            p.row_capacity = cap
+            try:
+                ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
+                                                  qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p),
+                                                  C.byref(total)))
+                return int(total.value)
+            except _lib.RowCapacityError:
+                # the reference emits at most max_alignments_per_id + 1 rows per candidate (:309-311)
+                bound = max(1, p.search_depth) * (p.max_alignments_per_id + 1)
+                if cap >= bound:
+                    raise
+                cap = min(cap * 8, bound)
 
     def match_batch(self, ht, queries, sort=True):
         """Match many queries in one device call.
@@ -64,10 +83,7 @@ class Matcher(object):
         nq = len(qoff) - 1
         p = self._params()
         ctx = ht._sync_device()
-        total = C.c_int64(0)
-        ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
-                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
-        rows = np.empty((int(total.value), 7), np.int32)
+        rows = np.empty((self._run(ctx, p, packed, nq, qoff), 7), np.int32)
         roff = np.zeros(nq + 1, np.int64)
         ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                roff.ctypes.data_as(C.POINTER(C.c_int64))))
@@ -92,10 +108,7 @@ class Matcher(object):
         p = self._params()
         p.publish_candidates = 1
         ctx = ht._sync_device()
-        total = C.c_int64(0)
-        ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
-                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
-        rows = np.empty((int(total.value), 7), np.int32)
+        rows = np.empty((self._run(ctx, p, packed, nq, qoff), 7), np.int32)
         roff = np.zeros(nq + 1, np.int64)
         ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                roff.ctypes.data_as(C.POINTER(C.c_int64))))
@@ -118,10 +131,7 @@ class Matcher(object):
         p = self._params()
         p.publish_candidates = 1
         ctx = ht._sync_device()
-        total = C.c_int64(0)
-        ctx.check(ctx.lib.afp_match_batch(ctx.h, qrows.ctypes.data if len(qrows) else None, 1, nq,
-                                          qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p), C.byref(total)))
-        rows = np.empty((int(total.value), 7), np.int32)
+        rows = np.empty((self._run(ctx, p, qrows, nq, qoff), 7), np.int32)
         roff = np.zeros(nq + 1, np.int64)
         ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                roff.ctypes.data_as(C.POINTER(C.c_int64))))

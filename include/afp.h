@@ -75,6 +75,10 @@ typedef struct {
                                   * the shard's full local top-search_depth ids of every query so
                                   * that one all-gather + afp_fetch_match_candidates can rebuild
                                   * the single-table result (audfprint_b200/dist.py)            */
+  int32_t row_capacity;          /* result rows kept per query (0 = 256).  The reference can emit up
+                                  * to search_depth * (max_alignments_per_id + 1); a query that
+                                  * produces more than this returns AFP_ERR_UNSUPPORTED and the
+                                  * caller retries with a larger capacity                       */
 } afp_matcher_params;
 
 /* ---- context --------------------------------------------------------------- */

@@ -289,3 +289,36 @@ def test_shard_batch_path_single_rank(golden_match):
     for i, s in enumerate(single):
         want = s[np.argsort(-s[:, 1], kind="stable")]
         assert np.array_equal(rows[off[i]:off[i + 1]], want)
+
+
+@pytest.mark.parametrize("density,fanout,shifts,f_sd,maxpks", [
+    (20.0, 3, 2, 30.0, 5), (20.0, 3, 3, 30.0, 5), (20.0, 3, 8, 30.0, 5),
+    (35.0, 5, 1, 20.0, 3), (50.0, 6, 4, 30.0, 8), (10.0, 1, 1, 45.0, 1), (70.0, 8, 1, 30.0, 16)])
+def test_non_default_analyzer_parameters_vs_oracle(density, fanout, shifts, f_sd, maxpks):
+    sigs = [synth_track(5000 + i, 9.0 + i) for i in range(4)]
+    an = Analyzer(density=density)
+    an.maxpairsperpeak, an.shifts, an.f_sd, an.maxpksperframe = fanout, shifts, f_sd, maxpks
+    got = an.fingerprint_batch(sigs)
+    for s, g in zip(sigs, got):
+        want = orc.fingerprint(pcm_to_float(s), density=density, fanout=fanout, shifts=shifts, f_sd=f_sd,
+                               maxpks=maxpks)
+        assert np.array_equal(g, want)
+    pk = an.find_peaks(sigs[0], 11025)
+    assert pk == orc.find_peaks(pcm_to_float(sigs[0]), density=density, f_sd=f_sd, maxpks=maxpks)
+
+
+def test_matcher_edge_parameters_vs_oracle(golden_match):
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, "db2")
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    qs = [gm["q%d_noisy/q" % j] for j in range(6)] + [np.zeros((0, 2), np.int32)]
+    for window, thresh, sdepth, maxal in [(0, 5, 100, 100), (3, 0, 5, 100), (1, 5, 1, 100), (2, 1, 100, 0),
+                                          (2, 5, 0, 100)]:
+        m = Matcher()
+        m.window, m.threshcount, m.search_depth, m.max_alignments_per_id = window, thresh, sdepth, maxal
+        got = m.match_batch(ht, qs)
+        for q, g in zip(qs, got):
+            w = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=window, threshcount=thresh,
+                                 search_depth=sdepth, max_alignments_per_id=maxal)
+            assert g.shape == w.shape and sorted(map(tuple, g)) == sorted(map(tuple, w)), (window, thresh, sdepth, maxal)
