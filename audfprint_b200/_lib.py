@@ -27,7 +27,7 @@ class RowCapacityError(AfpError):
 class AnalyzerParams(C.Structure):
     _fields_ = [("a_dec", C.c_double), ("hpf_pole", C.c_double), ("maxpksperframe", C.c_int32),
                 ("maxpairsperpeak", C.c_int32), ("targetdf", C.c_int32), ("mindt", C.c_int32),
-                ("targetdt", C.c_int32), ("shifts", C.c_int32)]
+                ("targetdt", C.c_int32), ("shifts", C.c_int32), ("spectrogram_fp32", C.c_int32)]
 
 
 class MatcherParams(C.Structure):

@@ -118,8 +118,11 @@ class Analyzer(object):
         self.soundfiletotaldur = 0.0
         self.soundfilecount = 0
         self.fail_on_error = True
-        # not in the reference: which GPU, and the pluggable file reader
+        # not in the reference: which GPU, the pluggable file reader, and the arithmetic of the
+        # spectrogram kernel: 'fp64' (default, results bit-identical to the reference) or 'fp32'
+        # (opt-in: K1 at HBM speed, magnitudes within 1e-5, a few files per thousand differ)
         self.device = device
+        self.precision = 'fp64'
         self.reader = _wav_reader
 
     # objects are pickled into worker processes by the reference CLI
@@ -132,6 +135,7 @@ class Analyzer(object):
 
     def __setstate__(self, st):
         self.__dict__.update(st)
+        self.__dict__.setdefault("precision", "fp64")
         if self.reader is None:
             self.reader = _wav_reader
 
@@ -144,12 +148,15 @@ class Analyzer(object):
         if self.n_fft != N_FFT or self.n_hop != N_HOP:
             raise ValueError("libafp is compiled for n_fft=512, n_hop=256")
         ctx = _lib.context(self.device)
+        if self.precision not in ('fp64', 'fp32'):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        fp32 = 1 if self.precision == 'fp32' else 0
         key = (float(self.density), float(self.f_sd), int(self.maxpksperframe), int(self.maxpairsperpeak),
-               int(self.targetdf), int(self.mindt), int(self.targetdt), int(shifts))
+               int(self.targetdf), int(self.mindt), int(self.targetdt), int(shifts), fp32)
         if ctx.analyzer_key != key:
             p = _lib.AnalyzerParams(self._a_dec(), HPF_POLE ** (1 / OVERSAMP), int(self.maxpksperframe),
                                     int(self.maxpairsperpeak), int(self.targetdf), int(self.mindt),
-                                    int(self.targetdt), int(shifts))
+                                    int(self.targetdt), int(shifts), fp32)
             # the very doubles the reference multiplies by (audfprint_analyze.py:279, :187-192)
             win = np.ascontiguousarray(np.hanning(self.n_fft + 2)[1:-1], dtype=np.float64)
             npts = self.n_fft // 2

@@ -48,8 +48,12 @@ int afp_create(afp_ctx** out, int device) {
     tw[1024 + 2 * i] = ci;
     tw[1024 + 2 * i + 1] = (double)(-0.5L * logl((long double)ci));
   }
+  std::vector<float> twf(2 * 512);
+  for (size_t i = 0; i < twf.size(); ++i) twf[i] = (float)tw[i];
   if (c->d_twid.reserve(tw.size() * sizeof(double)) != cudaSuccess ||
-      cudaMemcpy(c->d_twid.p, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(c->d_twid.p, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      c->d_twid_f.reserve(twf.size() * sizeof(float)) != cudaSuccess ||
+      cudaMemcpy(c->d_twid_f.p, twf.data(), twf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
     afp_destroy(c);
     return AFP_ERR_CUDA;
   }
@@ -63,7 +67,7 @@ void afp_destroy(afp_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (int i = 0; i <= AFP_NSTAGES; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  DevBuf* bufs[] = {&c->d_window, &c->d_gauss, &c->d_twid, &c->d_pcm_stage, &c->d_items, &c->d_tile_item, &c->d_file_col_base,
+  DevBuf* bufs[] = {&c->d_window, &c->d_window_f, &c->d_twid_f, &c->d_gauss, &c->d_twid, &c->d_pcm_stage, &c->d_items, &c->d_tile_item, &c->d_file_col_base,
                     &c->d_logs, &c->d_nyq, &c->d_tile_stats, &c->d_item_stats, &c->d_fwd_val, &c->d_fwd_bin,
                     &c->d_fwd_cnt, &c->d_pk_bin, &c->d_pk_cnt, &c->d_item_scols, &c->d_item_npeaks, &c->d_lm,
                     &c->d_col_cnt, &c->d_file_tot, &c->d_file_off, &c->d_hashes, &c->d_pk_off, &c->d_pk_rows,
@@ -155,6 +159,10 @@ int afp_set_analyzer(afp_ctx* c, const afp_analyzer_params* p, const double* win
   AFP_CUDA(c, c->d_gauss.reserve(g.size() * sizeof(double)));
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
   AFP_CUDA(c, cudaMemcpy(c->d_window.p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<float> wf(w.size());
+  for (size_t i = 0; i < w.size(); ++i) wf[i] = (float)w[i];
+  AFP_CUDA(c, c->d_window_f.reserve(wf.size() * sizeof(float)));
+  AFP_CUDA(c, cudaMemcpy(c->d_window_f.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   AFP_CUDA(c, cudaMemcpy(c->d_gauss.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
   c->ap = *p;
   c->analyzer_set = true;

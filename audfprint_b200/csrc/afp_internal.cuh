@@ -81,6 +81,8 @@ struct afp_ctx {
   bool analyzer_set = false;
   DevBuf d_window;   // 2 x 512 doubles: window, then window * 2^-15 (int16 PCM)
   DevBuf d_gauss;    // AFP_GAUSS_N doubles
+  DevBuf d_window_f; // float copies for the FP32 spectrogram mode
+  DevBuf d_twid_f;   // float2: tw256[p][r] (256), W512^k (256)
   DevBuf d_twid;     // double2 tables: tw256[p][r] (256), W512^k (256), log table (128)
 
   // batch state (valid after afp_fingerprint_batch)

@@ -31,7 +31,7 @@ struct PeakArgs {
   const ItemDesc* items;
   const ItemStats* stats;
   int item0;
-  const double* logs;     // [frames][256]
+  const void* logs;       // [frames][256], double (default) or float (FP32 spectrogram mode)
   const double* gauss;    // AFP_GAUSS_N
   double a_dec, pole;
   int maxpks;
@@ -121,16 +121,17 @@ __device__ __forceinline__ void hpf_step(const double (&l)[8], double (&z)[8], d
 
 // The column stream of one item: chunks of CH columns are TMA-bulk-copied into a ring of
 // NST shared-memory stages (one mbarrier each), NST chunks ahead of the consumer.
+template <typename R>
 struct ColRing {
-  double* buf;                 // NST * CH * 256 doubles
+  R* buf;                      // NST * CH * 256 values
   unsigned long long* bar;     // NST mbarriers
-  const double* src;           // column 0 of the item
+  const R* src;                // column 0 of the item
   int T;
   int lane;
 
   __device__ __forceinline__ void issue(int chunk) const {   // lane 0 only
     const int c0 = chunk * CH;
-    const uint32_t bytes = (uint32_t)min(CH, T - c0) * AFP_NBINS * sizeof(double);
+    const uint32_t bytes = (uint32_t)min(CH, T - c0) * AFP_NBINS * sizeof(R);
     unsigned long long* b = bar + (chunk % NST);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
@@ -156,12 +157,20 @@ struct ColRing {
   __device__ __forceinline__ void load(int t, double (&x)[8], bool consume) const {
     const int chunk = t / CH;
     if (t % CH == 0 || !consume) wait(chunk);
-    const double2* p = reinterpret_cast<const double2*>(buf + ((chunk % NST) * CH + t % CH) * AFP_NBINS) + 4 * lane;
+    const R* col = buf + ((chunk % NST) * CH + t % CH) * AFP_NBINS;
+    if (sizeof(R) == 8) {
+      const double2* p = reinterpret_cast<const double2*>(col) + 4 * lane;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double2 v = p[i];
-      x[2 * i] = v.x;
-      x[2 * i + 1] = v.y;
+      for (int i = 0; i < 4; ++i) {
+        const double2 v = p[i];
+        x[2 * i] = v.x;
+        x[2 * i + 1] = v.y;
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(col) + 2 * lane;
+      const float4 u = p[0], v = p[1];
+      x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+      x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
     }
     if (consume && (t % CH == CH - 1 || t == T - 1)) {
       __syncwarp();
@@ -170,9 +179,10 @@ struct ColRing {
   }
 };
 
+template <typename R>
 __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
   __shared__ __align__(16) double sE[AFP_GAUSS_PAD];
-  __shared__ __align__(128) double sCol[NST * CH * AFP_NBINS];
+  __shared__ __align__(128) R sCol[NST * CH * AFP_NBINS];
   __shared__ unsigned long long sBar[NST];
   const int lane = threadIdx.x;
   const int item = a.item0 + blockIdx.x;
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(32) afp_peaks_kernel(PeakArgs a) {
     }
     return;
   }
-  ColRing ring{sCol, sBar, a.logs + base * AFP_NBINS, T, lane};
+  ColRing<R> ring{sCol, sBar, reinterpret_cast<const R*>(a.logs) + base * AFP_NBINS, T, lane};
   if (lane == 0) {
     for (int i = 0; i < NST; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(sBar + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -392,7 +402,7 @@ int afp_launch_peaks(afp_ctx* c, int item0, int nitems) {
   a.items = c->d_items.as<ItemDesc>();
   a.stats = c->d_item_stats.as<ItemStats>();
   a.item0 = item0;
-  a.logs = c->d_logs.as<double>();
+  a.logs = c->d_logs.p;
   a.gauss = c->d_gauss.as<double>();
   a.a_dec = c->ap.a_dec;
   a.pole = c->ap.hpf_pole;
@@ -404,7 +414,8 @@ int afp_launch_peaks(afp_ctx* c, int item0, int nitems) {
   a.pk_cnt = c->d_pk_cnt.as<uint8_t>();
   a.item_scols = c->d_item_scols.as<int32_t>();
   a.item_npeaks = c->d_item_npeaks.as<int32_t>();
-  afp_peaks_kernel<<<nitems, 32, 0, c->stream>>>(a);
+  if (c->ap.spectrogram_fp32) afp_peaks_kernel<float><<<nitems, 32, 0, c->stream>>>(a);
+  else afp_peaks_kernel<double><<<nitems, 32, 0, c->stream>>>(a);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
   return AFP_OK;

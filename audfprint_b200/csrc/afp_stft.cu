@@ -49,6 +49,11 @@ struct StftArgs {
   double* nyq;            // [frames]
   double* tile_stats;     // [tiles][3]
   double* mag;            // optional [frames][257]
+  // FP32 spectrogram mode (opt-in, NOT bit-identical downstream)
+  const float* window_f;  // 512 (pre-scaled by 2^-15 for int16 PCM)
+  const float2* tw256_f;  // [p][r]
+  const float2* w512_f;   // 256
+  float* logs_f;          // [frames][256]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -366,6 +371,198 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
   }
 }
 
+
+// ---- FP32 variant of K1 (Analyzer.precision = 'fp32') -----------------------------------
+// Same decomposition, single precision throughout (FFT, |.|^2, log via MUFU), float
+// log-spectrogram out: half the output bytes, twice the FP32 lane rate, ~80 registers ->
+// three CTAs per SM.  Downstream decisions then see values that differ from the reference's
+// by ~1e-7 relative, so hashes are NOT guaranteed bit-identical (measured in bench.py).
+template <typename PcmT> struct PcmF32;
+template <> struct PcmF32<int16_t> {
+  __device__ static __forceinline__ void load2(const int16_t* p, float& a, float& b) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    a = (float)(short)(w & 0xffffu);
+    b = (float)((int)w >> 16);
+  }
+};
+template <> struct PcmF32<float> {
+  __device__ static __forceinline__ void load2(const float* p, float& a, float& b) {
+    const float2 w = *reinterpret_cast<const float2*>(p);
+    a = w.x;
+    b = w.y;
+  }
+};
+
+template <typename PcmT, bool WRITE_MAG>
+__global__ void __launch_bounds__(K1_THREADS, 3) afp_stft_f32_kernel(StftArgs a) {
+  constexpr int NBUF = PcmTraits<PcmT>::NBUF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_win = reinterpret_cast<float*>(smem_raw);                   // 512
+  float2* s_tw256 = reinterpret_cast<float2*>(s_win + 512);            // 256, [p][r]
+  float2* s_w512 = s_tw256 + 256;                                      // 256
+  float* s_xr = reinterpret_cast<float*>(s_w512 + 256);                // FT * XF
+  float* s_xi = s_xr + FT * XF;                                        // FT * XF
+  double* s_red = reinterpret_cast<double*>(s_xi + FT * XF);           // 3 * 8
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_red + 24);   // 2
+  PcmT* s_pcm = reinterpret_cast<PcmT*>(s_bar + 2);                    // NBUF * (FT+1)*256
+  constexpr int PCM_BUF = (FT + 1) * AFP_N_HOP;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 512; i += K1_THREADS) s_win[i] = a.window_f[i];
+  for (int i = tid; i < 256; i += K1_THREADS) {
+    s_tw256[i] = a.tw256_f[i];
+    s_w512[i] = a.w512_f[i];
+  }
+  __syncthreads();
+
+  const int g = tid >> 4, r = tid & 15, lane = tid & 31;
+  const int src_lane = (lane & 16) | ((16 - r) & 15);
+  uint32_t phases = 0u;
+
+  int tile = a.tile_begin + blockIdx.x;
+  if (tile >= a.tile_end) return;
+  const int G = gridDim.x;
+  TileInfo cur = make_tile<PcmT>(a, a.items[a.tile_item[tile]], tile);
+  TileInfo nxt = cur;
+  if (tile + G < a.tile_end) nxt = make_tile<PcmT>(a, a.items[a.tile_item[tile + G]], tile + G);
+  int item_nn = (tile + 2 * G < a.tile_end) ? a.tile_item[tile + 2 * G] : 0;
+  stage_tile<PcmT>(a, cur, s_pcm, s_bar);
+  int buf = 0;
+
+  for (; tile < a.tile_end; tile += G) {
+    const int next = tile + G;
+    if (NBUF == 2 && next < a.tile_end) stage_tile<PcmT>(a, nxt, s_pcm + (buf ^ 1) * PCM_BUF, s_bar + (buf ^ 1));
+    ItemDesc desc_nn = a.items[item_nn];
+    const int item_n3 = (tile + 3 * G < a.tile_end) ? a.tile_item[tile + 3 * G] : 0;
+    if (cur.tma) {
+      wait_bar(s_bar + buf, (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+    } else {
+      __syncthreads();
+    }
+    const bool active = g < cur.nft;
+    const int64_t frame = cur.frame0 + g;
+    float vmax = 0.0f, vsum = 0.0f;
+    int hmin = 0x7f800000;
+    float zr[16], zi[16];
+    if (active) {
+      const PcmT* fr = s_pcm + buf * PCM_BUF + g * AFP_N_HOP;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int i0 = 2 * (16 * q + r);
+        const float2 w = *reinterpret_cast<const float2*>(s_win + i0);
+        float x0, x1;
+        PcmF32<PcmT>::load2(fr + i0, x0, x1);
+        zr[q] = x0 * w.x;
+        zi[q] = x1 * w.y;
+      }
+      afp_fft16(zr, zi);
+      float* xr = s_xr + g * XF;
+      float* xi = s_xi + g * XF;
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const float2 w = s_tw256[p * 16 + r];
+        xr[p * XS + r] = zr[p] * w.x - zi[p] * w.y;
+        xi[p * XS + r] = zr[p] * w.y + zi[p] * w.x;
+      }
+    }
+    __syncwarp();
+    if (active) {
+      const float* xr = s_xr + g * XF + r * XS;
+      const float* xi = s_xi + g * XF + r * XS;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        zr[q] = xr[q];
+        zi[q] = xi[q];
+      }
+      afp_fft16(zr, zi);
+    }
+    {
+      float* out = a.logs_f + frame * AFP_NBINS;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        float c = __shfl_sync(0xffffffffu, zr[15 - s], src_lane);
+        float d = __shfl_sync(0xffffffffu, zi[15 - s], src_lane);
+        if (r == 0) {
+          c = zr[(16 - s) & 15];
+          d = zi[(16 - s) & 15];
+        }
+        if (active) {
+          const int k = r + 16 * s;
+          const float2 w = s_w512[k];
+          const float er = zr[s] + c, ei = zi[s] - d, orr = zi[s] + d, oi = c - zr[s];
+          const float pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
+          const float ar = er + pr, ai = ei + pi, br = er - pr, bi = ei - pi;
+          const float ssa = ar * ar + ai * ai, ssb = br * br + bi * bi;     // 4|X|^2
+          const float la = 0.5f * __logf(0.25f * ssa), lb = 0.5f * __logf(0.25f * ssb);
+          out[k] = la;
+          if (k != 0) out[256 - k] = lb; else a.nyq[frame] = (double)lb;
+          if (WRITE_MAG) {
+            a.mag[frame * 257 + k] = (double)sqrtf(0.25f * ssa);
+            a.mag[frame * 257 + 256 - k] = (double)sqrtf(0.25f * ssb);
+          }
+          vmax = fmaxf(vmax, fmaxf(ssa, ssb));
+          hmin = min(hmin, min(__float_as_int(ssa), __float_as_int(ssb)));
+          vsum += la + lb;
+        }
+      }
+      if (active && r == 0) {
+        const float2 w = s_w512[128];
+        const float er = 2.0f * zr[8], orr = 2.0f * zi[8];
+        const float ar = er + w.x * orr, ai = w.y * orr;
+        const float ss = ar * ar + ai * ai;
+        const float lg = 0.5f * __logf(0.25f * ss);
+        out[128] = lg;
+        if (WRITE_MAG) a.mag[frame * 257 + 128] = (double)sqrtf(0.25f * ss);
+        vmax = fmaxf(vmax, ss);
+        hmin = min(hmin, __float_as_int(ss));
+        vsum += lg;
+      }
+    }
+    hmin = __reduce_min_sync(0xffffffffu, hmin);
+    double vmin = hmin >= 0x7f800000 ? INFINITY
+                  : (hmin < 0x00800000 ? -INFINITY : (double)(0.5f * __logf(0.25f * __int_as_float(hmin))) - 1e-6);
+    double dmax = (double)vmax, dsum = (double)vsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    }
+    if (lane == 0) {
+      s_red[(tid >> 5) * 3 + 0] = dmax;
+      s_red[(tid >> 5) * 3 + 1] = vmin;
+      s_red[(tid >> 5) * 3 + 2] = dsum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double m = 0.0, mn = INFINITY, sm = 0.0;
+#pragma unroll
+      for (int w = 0; w < K1_THREADS / 32; ++w) {
+        m = fmax(m, s_red[w * 3 + 0]);
+        mn = fmin(mn, s_red[w * 3 + 1]);
+        sm += s_red[w * 3 + 2];
+      }
+      a.tile_stats[(size_t)tile * 3 + 0] = 0.25 * m;
+      a.tile_stats[(size_t)tile * 3 + 1] = mn;
+      a.tile_stats[(size_t)tile * 3 + 2] = sm;
+    }
+    if (NBUF == 2) buf ^= 1;
+    cur = nxt;
+    if (tile + 2 * G < a.tile_end) nxt = make_tile<PcmT>(a, desc_nn, tile + 2 * G);
+    item_nn = item_n3;
+    if (NBUF == 1 && next < a.tile_end) stage_tile<PcmT>(a, cur, s_pcm, s_bar);
+  }
+}
+
+constexpr size_t k1_f32_smem_bytes(size_t pcm_elem, int nbuf) {
+  return 512 * 4 + 256 * 8 * 2 + 2 * FT * XF * 4 + 24 * 8 + 16 + nbuf * (FT + 1) * 256 * pcm_elem;
+}
+
 // tile -> item table (one thread per item)
 __global__ void afp_tile_table_kernel(const ItemDesc* items, int nitems, int32_t* tile_item) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,8 +619,9 @@ __global__ void __launch_bounds__(256) afp_stats_kernel(const ItemDesc* items, i
 // floored tile sums of the flagged items: grid (items, FS_SPLIT); un-flagged items leave after
 // one load, a flagged item's tiles are dealt round-robin to its FS_SPLIT CTAs
 constexpr int FS_SPLIT = 8;
+template <typename R>
 __global__ void __launch_bounds__(256) afp_floorsum_kernel(const ItemDesc* items, int item0, const ItemStats* stats,
-                                                           const double* logs, const double* nyq,
+                                                           const R* logs, const double* nyq,
                                                            double* tile_stats) {
   __shared__ double s_part[8];
   const int item = item0 + blockIdx.x;
@@ -433,9 +631,9 @@ __global__ void __launch_bounds__(256) afp_floorsum_kernel(const ItemDesc* items
   const int ntiles = (it.nframes + FT - 1) / FT;
   for (int k = blockIdx.y; k < ntiles; k += FS_SPLIT) {
     const int t0 = k * FT, nft = min(FT, it.nframes - t0);
-    const double* L = logs + (size_t)(it.frame_base + t0) * AFP_NBINS;
+    const R* L = logs + (size_t)(it.frame_base + t0) * AFP_NBINS;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < nft * AFP_NBINS; i += 256) acc += fmax(L[i], st.logfloor);
+    for (int i = threadIdx.x; i < nft * AFP_NBINS; i += 256) acc += fmax((double)L[i], st.logfloor);
     if ((int)threadIdx.x < nft) acc += fmax(nyq[it.frame_base + t0 + threadIdx.x], st.logfloor);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -454,7 +652,8 @@ __global__ void __launch_bounds__(256) afp_floorsum_kernel(const ItemDesc* items
 // One thread per (item, bin); serial over time.  Not on the product path (the
 // peak kernel fuses this recursion); exists so that the test can compare the
 // sgram itself with the oracle.
-__global__ void afp_sgram_kernel(const ItemDesc* items, const ItemStats* stats, const double* logs,
+template <typename R>
+__global__ void afp_sgram_kernel(const ItemDesc* items, const ItemStats* stats, const R* logs,
                                  double pole, double* out) {
   const ItemDesc it = items[blockIdx.x];
   const ItemStats st = stats[blockIdx.x];
@@ -462,7 +661,7 @@ __global__ void afp_sgram_kernel(const ItemDesc* items, const ItemStats* stats, 
   double z = 0.0;
   for (int t = 0; t < it.nframes; ++t) {
     const size_t idx = (size_t)(it.frame_base + t) * AFP_NBINS + b;
-    double x = st.allzero ? 0.0 : __dsub_rn(fmax(logs[idx], st.logfloor), st.mean);
+    double x = st.allzero ? 0.0 : __dsub_rn(fmax((double)logs[idx], st.logfloor), st.mean);
     const double y = __dadd_rn(z, x);
     z = __dadd_rn(-x, __dmul_rn(pole, y));
     out[idx] = y;
@@ -497,9 +696,21 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
   a.nyq = c->d_nyq.as<double>();
   a.tile_stats = c->d_tile_stats.as<double>();
   a.mag = mag_out;
-  const int nctas = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * 2);
+  a.window_f = c->d_window_f.as<float>() + (dtype == AFP_PCM_I16 ? AFP_N_FFT : 0);
+  a.tw256_f = c->d_twid_f.as<float2>();
+  a.w512_f = c->d_twid_f.as<float2>() + 256;
+  a.logs_f = c->d_logs.as<float>();
+  const bool f32 = c->ap.spectrogram_fp32 != 0;
+  const int nctas = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * (f32 ? 3 : 2));
   const dim3 grid((unsigned)nctas), block(K1_THREADS);
   cudaError_t e;
+#define LAUNCH_F32(T, M)                                                                              \
+  do {                                                                                                \
+    const size_t smem = k1_f32_smem_bytes(sizeof(T), PcmTraits<T>::NBUF);                             \
+    e = cudaFuncSetAttribute(afp_stft_f32_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)smem);                                                              \
+    if (e == cudaSuccess) afp_stft_f32_kernel<T, M><<<grid, block, smem, c->stream>>>(a);             \
+  } while (0)
 #define LAUNCH(T, M)                                                                              \
   do {                                                                                            \
     const size_t smem = k1_smem_bytes(sizeof(T), PcmTraits<T>::NBUF);                             \
@@ -507,12 +718,19 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
                              (int)smem);                                                          \
     if (e == cudaSuccess) afp_stft_kernel<T, M><<<grid, block, smem, c->stream>>>(a);             \
   } while (0)
-  if (dtype == AFP_PCM_I16) {
+  if (f32) {
+    if (dtype == AFP_PCM_I16) {
+      if (mag_out) LAUNCH_F32(int16_t, true); else LAUNCH_F32(int16_t, false);
+    } else {
+      if (mag_out) LAUNCH_F32(float, true); else LAUNCH_F32(float, false);
+    }
+  } else if (dtype == AFP_PCM_I16) {
     if (mag_out) LAUNCH(int16_t, true); else LAUNCH(int16_t, false);
   } else {
     if (mag_out) LAUNCH(float, true); else LAUNCH(float, false);
   }
 #undef LAUNCH
+#undef LAUNCH_F32
   AFP_CUDA(c, e);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
@@ -526,8 +744,12 @@ int afp_launch_stats(afp_ctx* c, int item0, int nitems) {
   double* ts = c->d_tile_stats.as<double>();
   afp_stats_kernel<<<(nitems + 7) / 8, 256, 0, c->stream>>>(items, item0, nitems, ts, st, 0);
   AFP_CUDA(c, cudaGetLastError());
-  afp_floorsum_kernel<<<dim3((unsigned)nitems, FS_SPLIT), 256, 0, c->stream>>>(items, item0, st, c->d_logs.as<double>(),
-                                                                            c->d_nyq.as<double>(), ts);
+  if (c->ap.spectrogram_fp32)
+    afp_floorsum_kernel<float><<<dim3((unsigned)nitems, FS_SPLIT), 256, 0, c->stream>>>(
+        items, item0, st, c->d_logs.as<float>(), c->d_nyq.as<double>(), ts);
+  else
+    afp_floorsum_kernel<double><<<dim3((unsigned)nitems, FS_SPLIT), 256, 0, c->stream>>>(
+        items, item0, st, c->d_logs.as<double>(), c->d_nyq.as<double>(), ts);
   AFP_CUDA(c, cudaGetLastError());
   afp_stats_kernel<<<(nitems + 7) / 8, 256, 0, c->stream>>>(items, item0, nitems, ts, st, 1);
   AFP_CUDA(c, cudaGetLastError());
@@ -537,9 +759,12 @@ int afp_launch_stats(afp_ctx* c, int item0, int nitems) {
 
 int afp_launch_sgram(afp_ctx* c, double* sgram_out) {
   if (c->nitems == 0 || c->total_frames == 0) return AFP_OK;
-  afp_sgram_kernel<<<c->nitems, AFP_NBINS, 0, c->stream>>>(c->d_items.as<ItemDesc>(),
-                                                           c->d_item_stats.as<ItemStats>(),
-                                                           c->d_logs.as<double>(), c->ap.hpf_pole, sgram_out);
+  if (c->ap.spectrogram_fp32)
+    afp_sgram_kernel<float><<<c->nitems, AFP_NBINS, 0, c->stream>>>(
+        c->d_items.as<ItemDesc>(), c->d_item_stats.as<ItemStats>(), c->d_logs.as<float>(), c->ap.hpf_pole, sgram_out);
+  else
+    afp_sgram_kernel<double><<<c->nitems, AFP_NBINS, 0, c->stream>>>(
+        c->d_items.as<ItemDesc>(), c->d_item_stats.as<ItemStats>(), c->d_logs.as<double>(), c->ap.hpf_pole, sgram_out);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
   return AFP_OK;

@@ -63,6 +63,10 @@ typedef struct {
   int32_t mindt;           /* 2                                                  */
   int32_t targetdt;        /* 63                                                 */
   int32_t shifts;          /* Analyzer.shifts (1; 4 for match)                   */
+  int32_t spectrogram_fp32; /* 0 (default): FP64 STFT/log, results bit-identical to the
+                             * reference.  1: opt-in FP32 STFT + log + float spectrogram
+                             * (K1 at HBM speed; magnitudes within 1e-5 relative, hashes
+                             * NOT guaranteed identical - a few files per thousand differ) */
 } afp_analyzer_params;
 
 /* Matcher attributes (audfprint_match.py:96-122). */

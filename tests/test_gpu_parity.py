@@ -322,3 +322,25 @@ def test_matcher_edge_parameters_vs_oracle(golden_match):
             w = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=window, threshcount=thresh,
                                  search_depth=sdepth, max_alignments_per_id=maxal)
             assert g.shape == w.shape and sorted(map(tuple, g)) == sorted(map(tuple, w)), (window, thresh, sdepth, maxal)
+
+
+def test_fp32_spectrogram_mode_is_close_but_opt_in(golden_fp):
+    """Analyzer.precision = 'fp32': STFT magnitudes within the north-star tolerance (1e-5
+    relative), hashes nearly - not necessarily exactly - those of the FP64 path."""
+    an64, an32 = Analyzer(), Analyzer()
+    an32.precision = 'fp32'
+    pcm = synth_track(0, 30.0)
+    mag = an32.stft_magnitude(pcm)[:, ::SG_STRIDE]
+    want = golden_fp["s0_30s/mag_cols"]
+    assert np.max(np.abs(mag - want)) <= STFT_RTOL * np.max(want)
+    sg = an32.conditioned_sgram(pcm)[:, ::SG_STRIDE]
+    assert np.max(np.abs(sg - golden_fp["s0_30s/sgram_cols"])) < 1e-3
+    sigs = [synth_track(6000 + i, 20.0) for i in range(64)]
+    a = an64.fingerprint_batch(sigs)
+    b = an32.fingerprint_batch(sigs)
+    same = sum(np.array_equal(x, y) for x, y in zip(a, b))
+    inter = sum(len(set(map(tuple, x.tolist())) & set(map(tuple, y.tolist()))) for x, y in zip(a, b))
+    union = sum(len(set(map(tuple, x.tolist())) | set(map(tuple, y.tolist()))) for x, y in zip(a, b))
+    assert same >= 56 and inter / union > 0.995, (same, inter / union)
+    # the default stays FP64 and bit-exact
+    assert np.array_equal(an64.fingerprint_batch([pcm])[0], golden_fp["s0_30s/wf2h_s1"])
