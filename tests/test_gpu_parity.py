@@ -344,3 +344,18 @@ def test_fp32_spectrogram_mode_is_close_but_opt_in(golden_fp):
     assert same >= 56 and inter / union > 0.995, (same, inter / union)
     # the default stays FP64 and bit-exact
     assert np.array_equal(an64.fingerprint_batch([pcm])[0], golden_fp["s0_30s/wf2h_s1"])
+
+
+def test_long_lists_are_cut_into_device_calls():
+    sigs = [synth_track(7000 + i, 6.0 + (i % 3)) for i in range(9)]
+    an = Analyzer()
+    whole = an.fingerprint_batch(sigs)
+    an.max_frames_per_call = 700           # ~2 files per device call
+    parts = an.fingerprint_batch(sigs)
+    assert len(parts) == len(whole) and all(np.array_equal(a, b) for a, b in zip(parts, whole))
+    an.shifts = 4
+    an.max_frames_per_call = 1 << 23
+    w4 = an.fingerprint_batch(sigs)
+    an.max_frames_per_call = 3000
+    p4 = an.fingerprint_batch(sigs)
+    assert all(np.array_equal(a, b) for a, b in zip(p4, w4))
