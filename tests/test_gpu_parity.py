@@ -190,6 +190,31 @@ def test_match_file_level_api(tmp_path):
     assert len(an.wavfile2hashes(str(tmp_path / "missing.wav"))) == 0
 
 
+def test_ingest_batch_builds_the_same_table_as_per_file_ingest(tmp_path):
+    """One batched device call + per-file inserts == Analyzer.ingest file by file."""
+    import random
+    import wave
+    pcms = [synth_track(810 + i, 8.0 + i) for i in range(5)]
+    names = []
+    for i, pcm in enumerate(pcms):
+        fn = str(tmp_path / ("b%d.wav" % i))
+        with wave.open(fn, "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(11025)
+            w.writeframes(pcm.tobytes())
+        names.append(fn)
+    random.seed(5)
+    a_an, a = Analyzer(), HashTable(hashbits=12, depth=4)          # small: buckets overflow
+    for fn in names:
+        a_an.ingest(a, fn)
+    random.seed(5)
+    b_an, b = Analyzer(), HashTable(hashbits=12, depth=4)
+    counts = b_an.ingest_batch(b, names, pcms)
+    assert np.array_equal(a.table, b.table) and np.array_equal(a.counts, b.counts)
+    assert np.array_equal(a.hashesperid, b.hashesperid) and a.names == b.names
+    assert counts == [int(x) for x in b.hashesperid]
+    assert b_an.soundfilecount == 5 and abs(b_an.soundfiletotaldur - a_an.soundfiletotaldur) < 1e-9
+
+
 def test_chunked_host_pipeline_equals_resident_path():
     """>= 64 MB of host PCM takes the chunked copy/compute pipeline inside
     afp_fingerprint_batch; it must give exactly what the device-resident path gives."""
