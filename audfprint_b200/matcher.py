@@ -6,8 +6,12 @@ Host code keeps only what the reference does after the hot part: the final
 audfprint_match.py:335, so equal counts come out as they do in the reference on
 the same machine), `max_returns` truncation and message formatting.
 
-Not provided (optional second-wave flags): exact_count,
-find_time_range, illustrate — they raise NotImplementedError when set.
+The optional second-wave flags — exact_count, find_time_range and
+match_hashes(hashesfor=...) — take the hits (afp_get_hits) and the ranked candidate list
+(afp_match_batch, publish_candidates) from the device and finish on the host with the
+reference's per-candidate post-processing restated below (audfprint_match.py:149-244);
+that part is O(search_depth) small NumPy calls per query, as in the reference.
+illustrate (matplotlib) is not provided.
 """
 from __future__ import annotations
 
@@ -38,9 +42,8 @@ class Matcher(object):
         self.max_alignments_per_id = 100
 
     def _params(self):
-        if self.exact_count or self.find_time_range or self.illustrate:
-            raise NotImplementedError("exact_count / find_time_range / illustrate are not implemented "
-                                      "on the CUDA path (SURVEY.md §8f-4)")
+        if self.illustrate:
+            raise NotImplementedError("illustrate is not implemented (SURVEY.md §8f-4)")
         return _lib.MatcherParams(int(self.window), int(self.threshcount), int(self.search_depth),
                                   int(self.max_alignments_per_id), 0, 0)
 
@@ -82,6 +85,9 @@ class Matcher(object):
             packed = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros((0, 2), np.int32)
         nq = len(qoff) - 1
         p = self._params()
+        if self.exact_count or self.find_time_range:
+            out = [self._match_with_options(ht, packed[qoff[i]:qoff[i + 1]]) for i in range(nq)]
+            return [r[(-r[:, 1]).argsort(), ] for r in out] if sort else out
         ctx = ht._sync_device()
         rows = np.empty((self._run(ctx, p, packed, nq, qoff), 7), np.int32)
         roff = np.zeros(nq + 1, np.int64)
@@ -94,6 +100,89 @@ class Matcher(object):
                 r = r[(-r[:, 1]).argsort(), ]        # audfprint_match.py:335
             out.append(r)
         return out
+
+    # ---- exact_count / find_time_range / hashesfor (audfprint_match.py:149-244) ----
+    def _device_rows_and_candidates(self, ht, q):
+        """One query through afp_match_batch in publish mode: the approximate rows (rank order)
+        and the candidate list _best_count_ids would return (ids, rawcounts)."""
+        p = self._params()
+        p.publish_candidates = 1
+        ctx = ht._sync_device()
+        qoff = np.array([0, len(q)], np.int64)
+        rows = np.empty((self._run(ctx, p, q, 1, qoff), 7), np.int32)
+        roff = np.zeros(2, np.int64)
+        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        sd = max(int(self.search_depth), 1)
+        cand = np.zeros((1, sd, 3), np.float64)
+        cnts = np.zeros((1, 2), np.int32)
+        ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        depth = max(0, min(int(cnts[0, 1]), int(self.search_depth), int(cnts[0, 0])))
+        rows = rows[rows[:, 4] < depth]          # publish mode also reports the ids past maxdepth
+        return rows, cand[0, :depth, 0].astype(np.int64), cand[0, :depth, 1].astype(np.int64)
+
+    def _support(self, hits_by_id, tid, mode):
+        """Hits of track `tid` whose offset lies within `window` of `mode` (rows keep the
+        query-time order of hits_by_id)."""
+        h = hits_by_id.get(int(tid))
+        if h is None:
+            return np.zeros((0, 4), np.int32)
+        return h[np.abs(h[:, 1].astype(np.int64) - int(mode)) <= self.window]
+
+    def _time_range(self, hits_by_id, tid, mode):
+        """Quantile-trimmed query-time support of one alignment (audfprint_match.py:173-195)."""
+        t = self._support(hits_by_id, tid, mode)[:, 3]
+        return (t[int(len(t) * self.time_quantile)],
+                t[int(len(t) * (1.0 - self.time_quantile)) - 1])
+
+    @staticmethod
+    def _pair_keys(sup, timebits):
+        """Distinct (query time, hash) pairs, packed as the reference packs them (:166-167)."""
+        return np.unique(sup[:, 3] + (sup[:, 2].astype(np.int64) << timebits))
+
+    @staticmethod
+    def _split_by_id(hits):
+        """{id: that id's hits in query-time order}."""
+        if len(hits) == 0:
+            return {}
+        h = hits[np.lexsort((hits[:, 3], hits[:, 0]))]
+        cut = np.nonzero(np.diff(h[:, 0]))[0] + 1
+        return {int(part[0, 0]): part for part in np.split(h, cut)}
+
+    def _match_with_options(self, ht, q, hashesfor=None):
+        """Rows of match_hashes for exact_count / find_time_range (unsorted: candidate-rank
+        order), plus the matching (time, hash) pairs of row `hashesfor` of the SORTED result."""
+        q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 2)
+        hits = ht.get_hits(q)
+        approx, ids, raws = self._device_rows_and_candidates(ht, q)
+        by_id = self._split_by_id(hits)
+        if not self.exact_count:
+            rows = approx.copy()
+            if self.find_time_range:
+                for r in rows:
+                    r[5], r[6] = self._time_range(by_id, r[0], r[2])
+        else:
+            timebits = 1
+            if len(hits):
+                timebits = max(1, int(np.ceil(np.log(max(1, int(hits[:, 3].max()))) / np.log(2))))
+            out = []
+            for rank, (tid, raw) in enumerate(zip(ids, raws)):
+                dts = by_id[int(tid)][:, 1].astype(np.int64)
+                base = int(dts.min())
+                hist = np.bincount(dts - base)
+                rises = np.r_[True, hist[1:] >= hist[:-1], False]          # locmax (:48-65)
+                for mode in np.nonzero(rises[:-1] & ~rises[1:] & (hist >= self.threshcount))[0] + base:
+                    count = len(self._pair_keys(self._support(by_id, tid, mode), timebits))
+                    if count >= self.threshcount:
+                        lo, hi = self._time_range(by_id, tid, mode) if self.find_time_range else (0, 0)
+                        out.append([tid, count, mode, raw, rank, lo, hi])
+            rows = np.array(out, np.int32).reshape(-1, 7)
+        if hashesfor is None:
+            return rows
+        srt = rows[(-rows[:, 1]).argsort(), ]
+        timebits = max(1, int(np.ceil(np.log(max(1, int(hits[:, 3].max()))) / np.log(2))))
+        keys = self._pair_keys(self._support(by_id, srt[hashesfor, 0], srt[hashesfor, 2]), timebits)
+        return rows, np.c_[keys & ((1 << timebits) - 1), keys >> timebits]
 
     def match_batch_shard(self, ht, queries):
         """Table-shard side of a sharded match: `ht`'s device copy holds only
@@ -145,10 +234,12 @@ class Matcher(object):
     def match_hashes(self, ht, hashes, hashesfor=None):
         """Query hashes -> rows (id, filteredmatches, timoffs, rawmatches, origrank,
         mintime, maxtime), best first (audfprint_match.py:314-352)."""
-        if hashesfor is not None:
-            raise NotImplementedError("hashesfor needs _unique_match_hashes (SURVEY.md §8f-4)")
         q = np.asarray(hashes, dtype=np.int32).reshape(-1, 2)
-        return self.match_batch(ht, [q])[0]
+        if hashesfor is None:
+            return self.match_batch(ht, [q])[0]
+        self._params()
+        rows, pairs = self._match_with_options(ht, q, hashesfor)
+        return rows[(-rows[:, 1]).argsort(), ], pairs
 
     def match_file(self, analyzer, ht, filename, number=None):
         """Read, fingerprint and match one file (audfprint_match.py:354-379)."""

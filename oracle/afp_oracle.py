@@ -358,14 +358,74 @@ def offset_histogram_rows(hits: np.ndarray, ids, raws, window: int, threshcount:
     return np.array(rows, dtype=np.int32).reshape(-1, 7)
 
 
+def support_rows(hits: np.ndarray, id_: int, mode: int, window: int) -> np.ndarray:
+    """Hits of one id within +-window of an offset, in query-time order
+    (the selection of audfprint_match.py:163-165 and :184-188)."""
+    h = hits[np.argsort(hits[:, 3], kind="stable")]
+    return h[(h[:, 0] == id_) & (np.abs(h[:, 1].astype(np.int64) - mode) <= window)]
+
+
+def time_range(hits: np.ndarray, id_: int, mode: int, window: int, quantile: float = 0.02):
+    """Quantile-trimmed first / last query time supporting an alignment
+    (audfprint_match.py:173-195)."""
+    t = support_rows(hits, id_, mode, window)[:, 3]
+    n = len(t)
+    return int(t[int(n * quantile)]), int(t[int(n * (1.0 - quantile)) - 1])
+
+
+def pair_bits(hits: np.ndarray) -> int:
+    """Bits the reference reserves for the query time when packing (time, hash)
+    pairs - encpowerof2(max time), at least 1 (audfprint_match.py:46-48,157)."""
+    return max(1, int(np.ceil(np.log(max(1, int(np.max(hits[:, 3])))) / np.log(2))))
+
+
+def matching_pairs(hits: np.ndarray, id_: int, mode: int, window: int) -> np.ndarray:
+    """Distinct (query time, hash) pairs behind one alignment, as the reference packs
+    and unpacks them (audfprint_match.py:149-171) - int64 (n,2)."""
+    bits = pair_bits(hits)
+    sup = support_rows(hits, id_, mode, window)
+    packed = sorted(set(int(t) + (int(h) << bits) for t, h in zip(sup[:, 3], sup[:, 2])))
+    return np.array([[v & ((1 << bits) - 1), v >> bits] for v in packed], np.int64).reshape(-1, 2)
+
+
+def exact_rows(hits: np.ndarray, ids, raws, window: int, threshcount: int,
+               find_time_range: bool = False, quantile: float = 0.02) -> np.ndarray:
+    """exact_count branch (audfprint_match.py:197-239): every local maximum >= threshcount of a
+    candidate's offset histogram is an alignment; its count is the number of distinct
+    (query time, hash) pairs within +-window."""
+    rows = []
+    for rank, (id_, raw) in enumerate(zip(ids, raws)):
+        dts = hits[hits[:, 0] == id_, 1].astype(np.int64)
+        base = int(dts.min())
+        hist = np.bincount(dts - base)
+        for k in np.nonzero(local_max_mask(hist) & (hist >= threshcount))[0]:
+            mode = int(k) + base
+            n = len(matching_pairs(hits, id_, mode, window))
+            if n >= threshcount:
+                lo, hi = time_range(hits, id_, mode, window, quantile) if find_time_range else (0, 0)
+                rows.append([int(id_), n, mode, int(raw), rank, lo, hi])
+    return np.array(rows, dtype=np.int32).reshape(-1, 7)
+
+
 def match_hashes(table, counts, hashbits, depth, maxtimebits, hashesperid, q,
-                 window=1, threshcount=5, search_depth=100, max_alignments_per_id=100) -> np.ndarray:
-    """get_hits -> rank_candidates -> offset_histogram_rows -> sort by count
+                 window=1, threshcount=5, search_depth=100, max_alignments_per_id=100,
+                 exact_count=False, find_time_range=False, quantile=0.02, hashesfor=None):
+    """get_hits -> rank_candidates -> offset_histogram_rows (or exact_rows) -> sort by count
     descending (stable; the reference's final argsort, audfprint_match.py:335,
-    is unstable so equal counts are implementation-defined there)."""
+    is unstable so equal counts are implementation-defined there).
+    With hashesfor=k also returns the matching pairs of sorted row k (:347-352)."""
     hits = get_hits(table, counts, hashbits, depth, maxtimebits, q)
     if hits.shape[0] == 0:
         return np.zeros((0, 7), np.int32)
     ids, raws = rank_candidates(hits, hashesperid, threshcount, search_depth)
-    rows = offset_histogram_rows(hits, ids, raws, window, threshcount, max_alignments_per_id)
-    return rows[np.argsort(-rows[:, 1], kind="stable")]
+    if exact_count:
+        rows = exact_rows(hits, ids, raws, window, threshcount, find_time_range, quantile)
+    else:
+        rows = offset_histogram_rows(hits, ids, raws, window, threshcount, max_alignments_per_id)
+        if find_time_range:
+            for r in rows:
+                r[5], r[6] = time_range(hits, int(r[0]), int(r[2]), window, quantile)
+    rows = rows[np.argsort(-rows[:, 1], kind="stable")]
+    if hashesfor is None:
+        return rows
+    return rows, matching_pairs(hits, int(rows[hashesfor, 0]), int(rows[hashesfor, 2]), window)

@@ -25,6 +25,22 @@ def golden_match():
     return np.load(os.path.join(GOLDEN, "match.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_options():
+    """Reference Matcher output with exact_count / find_time_range / hashesfor
+    (oracle/make_golden_options.py)."""
+    return np.load(os.path.join(GOLDEN, "match_options.npz"))
+
+
+def option_ties(hits, hpi, rows, thresh, sdepth):
+    """(candidate order ambiguous, row order ambiguous) for one reference result."""
+    ids, raw = np.unique(hits[:, 0], return_counts=True)
+    wtd = raw / np.asarray(hpi)[ids].astype(float)
+    dep = min(int(np.count_nonzero(raw > thresh)), sdepth)
+    srt = np.sort(wtd)[::-1][:dep + 1]
+    return bool(dep and np.any(srt[:-1] == srt[1:])), bool(len(np.unique(rows[:, 1])) != len(rows))
+
+
 def expand_table(gm, db):
     """Rebuild dense (table, counts) arrays from the sparse golden storage."""
     hashbits, depth, mtb = (int(x) for x in gm[db + "/params"])

@@ -115,7 +115,7 @@ def test_objects_pickle_without_device_state():
     assert a.density == 70.0 and a.shifts == 1 and a.maxpksperframe == 5
     m = pickle.loads(pickle.dumps(Matcher()))
     assert m.window == 1 and m.threshcount == 5
-    m.exact_count = True
+    m.illustrate = True
     with pytest.raises(NotImplementedError):
         m._params()
 
@@ -154,3 +154,43 @@ def test_saved_database_has_the_reference_class_path(tmp_path):
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
         assert "['x'] 3 [[0, 1, 5, 0], [0, 2, 5, 0]]" in out.stdout
+
+
+@pytest.mark.parametrize("db", ["db", "db2"])
+def test_matcher_option_postprocessing_host_logic(golden_match, golden_options, db, monkeypatch):
+    """Matcher's exact_count / find_time_range / hashesfor host stage, fed with the reference's
+    own hits and the oracle's candidate list in place of the two device calls (those are
+    checked on the GPU in test_gpu_parity.py)."""
+    from oracle import afp_oracle as orc
+    from tests.conftest import expand_table, option_ties
+    gm, go = golden_match, golden_options
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    nexact = 0
+    for j in range(cases.DB_QUERIES):
+        for tag in ("clean", "noisy"):
+            key = "q%d_%s" % (j, tag)
+            q = gm[key + "/q"]
+            hits = gm["%s/%s/hits" % (db, key)]
+            for cfg in ("tr", "ex", "extr", "trb"):
+                exact, trange, window, thresh, sdepth = (int(x) for x in go["cfg_" + cfg])
+                m = Matcher()
+                m.window, m.threshcount, m.search_depth = window, thresh, sdepth
+                m.exact_count, m.find_time_range = bool(exact), bool(trange)
+                ids, raws = orc.rank_candidates(hits, hpi, thresh, sdepth)
+                approx = orc.offset_histogram_rows(hits, ids, raws, window, thresh)
+                monkeypatch.setattr(m, "_device_rows_and_candidates", lambda ht, q_: (approx, ids, raws))
+
+                class _HT:                       # stands in for the device probe
+                    def get_hits(self, q_):
+                        return hits
+                want = go["%s/%s/rows_%s" % (db, key, cfg)]
+                tie_w, tie_c = option_ties(hits, hpi, want, thresh, sdepth)
+                if len(want) and not tie_w and not tie_c:
+                    rows, pairs = m.match_hashes(_HT(), q, hashesfor=0)
+                    assert np.array_equal(rows, want), (db, key, cfg)
+                    assert np.array_equal(pairs, go["%s/%s/pairs_%s" % (db, key, cfg)])
+                    nexact += 1
+                else:
+                    rows = m.match_batch(_HT(), [q])[0]
+                    assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1])
+    assert nexact > 15

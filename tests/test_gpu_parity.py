@@ -154,6 +154,43 @@ def test_get_hits_and_match_vs_reference_golden(golden_match, db):
     assert nexact > 15
 
 
+@pytest.mark.parametrize("db", ["db", "db2"])
+def test_matcher_options_vs_reference_golden(golden_match, golden_options, db):
+    """exact_count / find_time_range / hashesfor: device hits + device candidate list, host
+    finish - against the live reference's rows (oracle/make_golden_options.py)."""
+    from tests.conftest import option_ties
+    gm, go = golden_match, golden_options
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    ht.names = ["track%d" % i for i in range(cases.DB_NTRACKS)]
+    nexact = 0
+    for cfg in ("tr", "ex", "extr", "trb"):
+        exact, trange, window, thresh, sdepth = (int(x) for x in go["cfg_" + cfg])
+        m = Matcher()
+        m.window, m.threshcount, m.search_depth = window, thresh, sdepth
+        m.exact_count, m.find_time_range = bool(exact), bool(trange)
+        for j in range(cases.DB_QUERIES):
+            for tag in ("clean", "noisy"):
+                key = "q%d_%s" % (j, tag)
+                q = gm[key + "/q"]
+                want = go["%s/%s/rows_%s" % (db, key, cfg)]
+                tie_w, tie_c = option_ties(gm["%s/%s/hits" % (db, key)], hpi, want, thresh, sdepth)
+                orows = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, q, window=window,
+                                         threshcount=thresh, search_depth=sdepth,
+                                         exact_count=bool(exact), find_time_range=bool(trange))
+                if len(want) and not tie_w and not tie_c:
+                    rows, pairs = m.match_hashes(ht, q, hashesfor=0)
+                    assert np.array_equal(rows, want), (db, key, cfg)
+                    assert np.array_equal(pairs, go["%s/%s/pairs_%s" % (db, key, cfg)])
+                    nexact += 1
+                else:
+                    rows = m.match_hashes(ht, q)
+                    assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1])
+                assert sorted(map(tuple, rows)) == sorted(map(tuple, orows)), (db, key, cfg)
+    assert nexact > 40
+
+
 def test_match_file_level_api(tmp_path):
     """wavfile2hashes / ingest / match_file / file_match_to_msgs through WAV files."""
     import wave
