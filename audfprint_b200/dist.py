@@ -196,30 +196,38 @@ def pack_shard_batch(cand, counts, rows, row_off, row_cap: int) -> np.ndarray:
 def merge_shard_batch(gathered: np.ndarray, search_depth: int, row_cap: int):
     """Vectorised merge_sharded_results over a whole batch.
     gathered: (S, nq, W) packed records of all shards.  Returns (rows (R,7) int32 in
-    (query, global rank) order, row_off (nq+1))."""
+    (query, global rank) order, row_off (nq+1)).
+
+    No sort of the merged candidate lists: only ids that produced rows need a global rank, and
+    the rank of id x is the number of published candidates that order before it by (weight desc,
+    id desc) - found by one bisection per (row, shard) in that shard's already ordered list."""
     S, nq, _ = gathered.shape
     sd = max(int(search_depth), 1)
     depth = np.minimum(gathered[:, :, 0].sum(axis=0), search_depth).astype(np.int64)        # (nq,)
     ncand = gathered[:, :, 1].astype(np.int64)                                               # (S, nq)
     cand = gathered[:, :, 3:3 + 3 * sd].reshape(S, nq, sd, 3)
-    valid = np.arange(sd)[None, None, :] < ncand[:, :, None]
-    ids = np.where(valid, cand[..., 0], -1.0).transpose(1, 0, 2).reshape(nq, S * sd)
-    wts = np.where(valid, cand[..., 2], -np.inf).transpose(1, 0, 2).reshape(nq, S * sd)
-    o1 = np.argsort(-ids, axis=1, kind="stable")                                             # id desc
-    o2 = np.argsort(-np.take_along_axis(wts, o1, axis=1), axis=1, kind="stable")              # weight desc
-    order = np.take_along_axis(o1, o2, axis=1)
-    sorted_ids = np.take_along_axis(ids, order, axis=1)                                      # (nq, S*sd)
     nrows = gathered[:, :, 2].astype(np.int64)                                               # (S, nq)
     rows = gathered[:, :, 3 + 3 * sd:].reshape(S, nq, row_cap, 7)
-    rvalid = np.arange(row_cap)[None, None, :] < nrows[:, :, None]
-    s_idx, q_idx, k_idx = np.nonzero(rvalid)
+    s_idx, q_idx, k_idx = np.nonzero(np.arange(row_cap)[None, None, :] < nrows[:, :, None])
     if len(q_idx) == 0:
         return np.zeros((0, 7), np.int32), np.zeros(nq + 1, np.int64)
     r = rows[s_idx, q_idx, k_idx].astype(np.int64)                                            # (R0, 7)
-    match = sorted_ids[q_idx] == r[:, :1]                                                     # (R0, S*sd)
-    pos = np.argmax(match, axis=1)
-    keep = match.any(axis=1) & (pos < depth[q_idx])
-    r, q_idx, pos, s_idx, k_idx = r[keep], q_idx[keep], pos[keep], s_idx[keep], k_idx[keep]
+    w_x = cand[s_idx, q_idx, r[:, 4], 2][:, None]    # column 4 = rank in the shard's own list
+    i_x = r[:, :1].astype(np.float64)
+    shard = np.arange(S)[None, :]
+    lo = np.zeros((len(r), S), np.int64)
+    hi = ncand[:, q_idx].T.copy()                                                             # (R0, S)
+    for _ in range(int(sd).bit_length()):
+        active = lo < hi
+        mid = (lo + hi) >> 1
+        at = np.minimum(mid, sd - 1)
+        w = cand[shard, q_idx[:, None], at, 2]
+        before = (w > w_x) | ((w == w_x) & (cand[shard, q_idx[:, None], at, 0] > i_x))
+        lo = np.where(active & before, mid + 1, lo)
+        hi = np.where(active & ~before, mid, hi)
+    pos = lo.sum(axis=1)
+    keep = pos < depth[q_idx]
+    r, q_idx, pos, k_idx = r[keep], q_idx[keep], pos[keep], k_idx[keep]
     r[:, 4] = pos
     o = np.lexsort((k_idx, pos, q_idx))            # query, then global rank, then emission order
     r, q_idx = r[o], q_idx[o]

@@ -95,3 +95,28 @@ def test_shard_helpers_single_process():
     assert afd.interleave_shards([[0, 2, 4], [1, 3]], 5) == [0, 1, 2, 3, 4]
     empty = afd.merge_sharded_results([{"n_above": 0, "cand": np.zeros((0, 3)), "rows": np.zeros((0, 7))}], 100)
     assert empty.shape == (0, 7)
+
+
+@pytest.mark.parametrize("db,nshards", [("db", 3), ("db2", 2), ("db", 5)])
+def test_batch_merge_equals_per_query_merge(golden_match, db, nshards):
+    """merge_shard_batch (rank counting over packed records, the multi-GPU product path)
+    == merge_sharded_results query by query == the single-table rows."""
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    for cfg in ("a", "b"):
+        window, thresh, sdepth = (int(x) for x in gm["cfg_" + cfg])
+        per_shard = []
+        for s in range(nshards):
+            lo, hi = afd.id_range(len(hpi), s, nshards)
+            per_shard.append([shard_record(table, counts, hashbits, depth, mtb, hpi, gm[k + "/q"], lo, hi,
+                                           window, thresh, sdepth) for k in keys])
+        gathered = np.stack([afd.pack_shard_records(recs, sdepth, 128) for recs in per_shard])
+        rows, off = afd.merge_shard_batch(gathered, sdepth, 128)
+        assert off[-1] == len(rows) and len(off) == len(keys) + 1
+        for qi, k in enumerate(keys):
+            one = afd.merge_sharded_results([per_shard[s][qi] for s in range(nshards)], sdepth)
+            assert np.array_equal(rows[off[qi]:off[qi + 1]], one), (db, cfg, k)
+            want = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, gm[k + "/q"], window=window,
+                                    threshcount=thresh, search_depth=sdepth)
+            assert np.array_equal(one[np.argsort(-one[:, 1], kind="stable")], want)
