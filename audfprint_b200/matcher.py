@@ -105,18 +105,7 @@ class Matcher(object):
     def _device_rows_and_candidates(self, ht, q):
         """One query through afp_match_batch in publish mode: the approximate rows (rank order)
         and the candidate list _best_count_ids would return (ids, rawcounts)."""
-        p = self._params()
-        p.publish_candidates = 1
-        ctx = ht._sync_device()
-        qoff = np.array([0, len(q)], np.int64)
-        rows = np.empty((self._run(ctx, p, q, 1, qoff), 7), np.int32)
-        roff = np.zeros(2, np.int64)
-        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
-                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
-        sd = max(int(self.search_depth), 1)
-        cand = np.zeros((1, sd, 3), np.float64)
-        cnts = np.zeros((1, 2), np.int32)
-        ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        rows, _, cand, cnts = self._publish_call(ht, q, np.array([0, len(q)], np.int64))
         depth = max(0, min(int(cnts[0, 1]), int(self.search_depth), int(cnts[0, 0])))
         rows = rows[rows[:, 4] < depth]          # publish mode also reports the ids past maxdepth
         return rows, cand[0, :depth, 0].astype(np.int64), cand[0, :depth, 1].astype(np.int64)
@@ -184,6 +173,23 @@ class Matcher(object):
         keys = self._pair_keys(self._support(by_id, srt[hashesfor, 0], srt[hashesfor, 2]), timebits)
         return rows, np.c_[keys & ((1 << timebits) - 1), keys >> timebits]
 
+    def _publish_call(self, ht, qrows, qoff):
+        """afp_match_batch with publish_candidates: (rows (R,7) with LOCAL ranks, row offsets,
+        cand (nq, search_depth, 3) f64 [id, raw, weight], counts (nq, 2) i32 [entries, n_above])."""
+        nq = len(qoff) - 1
+        p = self._params()
+        p.publish_candidates = 1
+        ctx = ht._sync_device()
+        rows = np.empty((self._run(ctx, p, qrows, nq, qoff), 7), np.int32)
+        roff = np.zeros(nq + 1, np.int64)
+        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
+        cand = np.zeros((nq, max(int(self.search_depth), 1), 3), np.float64)
+        cnts = np.zeros((nq, 2), np.int32)
+        if nq:
+            ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        return rows, roff, cand, cnts
+
     def match_batch_shard(self, ht, queries):
         """Table-shard side of a sharded match: `ht`'s device copy holds only
         this rank's id range.  Returns one record per query for dist.merge_sharded_results:
@@ -193,21 +199,9 @@ class Matcher(object):
         if arrs:
             qoff[1:] = np.cumsum([len(a) for a in arrs])
         packed = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros((0, 2), np.int32)
-        nq = len(arrs)
-        p = self._params()
-        p.publish_candidates = 1
-        ctx = ht._sync_device()
-        rows = np.empty((self._run(ctx, p, packed, nq, qoff), 7), np.int32)
-        roff = np.zeros(nq + 1, np.int64)
-        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
-                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
-        sd = max(int(self.search_depth), 1)
-        cand = np.zeros((nq, sd, 3), np.float64)
-        cnts = np.zeros((nq, 2), np.int32)
-        if nq:
-            ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        rows, roff, cand, cnts = self._publish_call(ht, packed, qoff)
         return [{"n_above": int(cnts[i, 1]), "cand": cand[i, :cnts[i, 0]].copy(),
-                 "rows": rows[roff[i]:roff[i + 1]].copy()} for i in range(nq)]
+                 "rows": rows[roff[i]:roff[i + 1]].copy()} for i in range(len(arrs))]
 
     def match_batch_shard_packed(self, ht, packed_queries, row_cap=16):
         """match_batch_shard for a packed (rows, offsets) query batch, returning the fixed-size
@@ -216,19 +210,7 @@ class Matcher(object):
         qrows, qoff = packed_queries
         qrows = np.ascontiguousarray(qrows, dtype=np.int32).reshape(-1, 2)
         qoff = np.ascontiguousarray(qoff, dtype=np.int64)
-        nq = len(qoff) - 1
-        p = self._params()
-        p.publish_candidates = 1
-        ctx = ht._sync_device()
-        rows = np.empty((self._run(ctx, p, qrows, nq, qoff), 7), np.int32)
-        roff = np.zeros(nq + 1, np.int64)
-        ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
-                                               roff.ctypes.data_as(C.POINTER(C.c_int64))))
-        sd = max(int(self.search_depth), 1)
-        cand = np.zeros((nq, sd, 3), np.float64)
-        cnts = np.zeros((nq, 2), np.int32)
-        if nq:
-            ctx.check(ctx.lib.afp_fetch_match_candidates(ctx.h, cand.ctypes.data, cnts.ctypes.data, 1))
+        rows, roff, cand, cnts = self._publish_call(ht, qrows, qoff)
         return afd.pack_shard_batch(cand, cnts, rows, roff, row_cap)
 
     def match_hashes(self, ht, hashes, hashesfor=None):
