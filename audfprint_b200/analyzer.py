@@ -29,41 +29,31 @@ N_FFT = 512
 N_HOP = 256
 HPF_POLE = 0.98
 
-# hash packing (audfprint_analyze.py:69-78)
+# hash layout (audfprint_analyze.py:69-78): bin1 in 8 bits, signed bin difference in 6, frame gap in 6
 F1_BITS, DF_BITS, DT_BITS = 8, 6, 6
-B1_MASK = (1 << F1_BITS) - 1
-B1_SHIFT = DF_BITS + DT_BITS
-DF_MASK = (1 << DF_BITS) - 1
-DF_SHIFT = DT_BITS
-DT_MASK = (1 << DT_BITS) - 1
+B1_SHIFT, DF_SHIFT = DF_BITS + DT_BITS, DT_BITS
+B1_MASK, DF_MASK, DT_MASK = (1 << F1_BITS) - 1, (1 << DF_BITS) - 1, (1 << DT_BITS) - 1
 
 
 def landmarks2hashes(landmarks):
     """(time, bin1, bin2, dtime) rows -> int32 (L,2) [time, hash]
     (audfprint_analyze.py:81-96).  Pure bit packing of values the device
     produced; kept on the host for API parity (<1 % of the reference's time)."""
-    landmarks = np.array(landmarks)
-    if landmarks.shape[0] == 0:
-        return np.zeros((0, 2), dtype=np.int32)
-    hashes = np.zeros((landmarks.shape[0], 2), dtype=np.int32)
-    hashes[:, 0] = landmarks[:, 0]
-    hashes[:, 1] = (((landmarks[:, 1] & B1_MASK) << B1_SHIFT)
-                    | (((landmarks[:, 2] - landmarks[:, 1]) & DF_MASK) << DF_SHIFT)
-                    | (landmarks[:, 3] & DT_MASK))
-    return hashes
+    lm = np.asarray(landmarks, dtype=np.int64).reshape(-1, 4)
+    t, f1, f2, dt = lm[:, 0], lm[:, 1], lm[:, 2], lm[:, 3]
+    packed = ((f1 & B1_MASK) << B1_SHIFT) | (((f2 - f1) & DF_MASK) << DF_SHIFT) | (dt & DT_MASK)
+    return np.stack([t, packed], axis=1).astype(np.int32)
 
 
 def hashes2landmarks(hashes):
-    """Inverse of landmarks2hashes (audfprint_analyze.py:99-112)."""
-    out = []
-    for time_, hash_ in hashes:
-        dtime = hash_ & DT_MASK
-        bin1 = (hash_ >> B1_SHIFT) & B1_MASK
-        dbin = (hash_ >> DF_SHIFT) & DF_MASK
-        if dbin >= (1 << (DF_BITS - 1)):
-            dbin -= (1 << DF_BITS)
-        out.append((time_, bin1, bin1 + dbin, dtime))
-    return out
+    """Inverse of landmarks2hashes (audfprint_analyze.py:99-112): list of
+    (time, bin1, bin2, dtime) tuples."""
+    h = np.asarray(hashes, dtype=np.int64).reshape(-1, 2)
+    word = h[:, 1]
+    f1 = (word >> B1_SHIFT) & B1_MASK
+    df = (word >> DF_SHIFT) & DF_MASK
+    df = df - ((df >> (DF_BITS - 1)) << DF_BITS)          # sign-extend the 6-bit difference
+    return list(zip(h[:, 0].tolist(), f1.tolist(), (f1 + df).tolist(), (word & DT_MASK).tolist()))
 
 
 def _wav_reader(filename, sr=None, channels=None):
@@ -102,22 +92,16 @@ def _as_pcm(d):
 class Analyzer(object):
     """Parameters + methods of the reference Analyzer (audfprint_analyze.py:115-151)."""
 
+    # attribute -> default, as set by audfprint_analyze.py:118-147
+    _REFERENCE_DEFAULTS = dict(target_sr=11025, n_fft=N_FFT, n_hop=N_HOP, shifts=1, f_sd=30.0,
+                               maxpksperframe=5, maxpairsperpeak=3, targetdf=31, mindt=2, targetdt=63,
+                               soundfiledur=0.0, soundfiletotaldur=0.0, soundfilecount=0,
+                               fail_on_error=True)
+
     def __init__(self, density=DENSITY, device=None):
         self.density = density
-        self.target_sr = 11025
-        self.n_fft = N_FFT
-        self.n_hop = N_HOP
-        self.shifts = 1
-        self.f_sd = 30.0
-        self.maxpksperframe = 5
-        self.maxpairsperpeak = 3
-        self.targetdf = 31
-        self.mindt = 2
-        self.targetdt = 63
-        self.soundfiledur = 0.0
-        self.soundfiletotaldur = 0.0
-        self.soundfilecount = 0
-        self.fail_on_error = True
+        for attr, default in self._REFERENCE_DEFAULTS.items():
+            setattr(self, attr, default)
         # not in the reference: which GPU, the pluggable file reader, and the arithmetic of the
         # spectrogram kernel: 'fp64' (default, results bit-identical to the reference) or 'fp32'
         # (opt-in: K1 at HBM speed, magnitudes within 1e-5, a few files per thousand differ)

@@ -78,18 +78,13 @@ class HashTable(object):
         self._version = 0            # bumped on every mutation
         if filename is not None:
             self.load(filename)
-        else:
-            self.hashbits = hashbits
-            self.depth = depth
-            self.maxtimebits = _bitsfor(maxtime)
-            size = 2 ** hashbits
-            self.table = np.zeros((size, depth), dtype=np.uint32)
-            self.counts = np.zeros(size, dtype=np.int32)
-            self.names = []
-            self.hashesperid = np.zeros(0, np.uint32)
-            self.params = {}
-            self.ht_version = HT_VERSION
-            self.dirty = True
+            return
+        # empty table of 2^hashbits buckets x depth slots (hash_table.py:60-81)
+        self.hashbits, self.depth, self.maxtimebits = hashbits, depth, _bitsfor(maxtime)
+        self.table = np.zeros((1 << hashbits, depth), dtype=np.uint32)
+        self.counts = np.zeros(1 << hashbits, dtype=np.int32)
+        self.names, self.hashesperid = [], np.zeros(0, np.uint32)
+        self.params, self.ht_version, self.dirty = {}, HT_VERSION, True
 
     # ---- pickling: only plain host state travels (reference pickles the object) ----
     def __getstate__(self):
@@ -109,10 +104,9 @@ class HashTable(object):
 
     def reset(self):
         """Empty the table, keep the geometry (hash_table.py:83-89)."""
-        self.table[:, :] = 0
-        self.counts[:] = 0
-        self.names = []
-        self.hashesperid = np.zeros(0, np.uint32)
+        self.table.fill(0)
+        self.counts.fill(0)
+        self.names, self.hashesperid = [], np.zeros(0, np.uint32)
         self._touch()
 
     # ---- mutation (host) ---------------------------------------------------------
@@ -153,41 +147,47 @@ class HashTable(object):
         self._touch()
 
     def merge(self, ht):
-        """Merge another table, ids offset by our size (hash_table.py:291-323)."""
-        assert self.maxtimebits == ht.maxtimebits
-        ncurrent = len(self.names)
+        """Append another table's tracks after ours (hash_table.py:291-323): its ids move up by
+        len(self.names); a bucket that still fits keeps every entry (ours first), a bucket that
+        does not keeps `depth` entries chosen by np.random.permutation - drawn bucket by bucket in
+        ascending hash order, as the reference does, so the same seed gives the same table."""
+        if self.maxtimebits != ht.maxtimebits:
+            raise AssertionError("tables disagree on maxtimebits (%d vs %d)" % (self.maxtimebits, ht.maxtimebits))
+        shift = np.uint32(len(self.names) << self.maxtimebits)
         self.names += ht.names
-        self.hashesperid = np.append(self.hashesperid, ht.hashesperid)
-        idoffset = (1 << self.maxtimebits) * ncurrent
-        for hash_ in np.nonzero(ht.counts)[0]:
-            allvals = np.r_[self.table[hash_, :self.counts[hash_]],
-                            ht.table[hash_, :ht.counts[hash_]] + idoffset]
-            if len(allvals) > self.depth:
-                somevals = np.random.permutation(allvals)[:self.depth]
-                self.table[hash_, ] = somevals
-                self.counts[hash_] += ht.counts[hash_]
-            else:
-                self.table[hash_, :len(allvals)] = allvals
-                self.counts[hash_] = len(allvals)
+        self.hashesperid = np.concatenate([self.hashesperid, ht.hashesperid]).astype(np.uint32)
+        buckets = np.nonzero(ht.counts)[0]
+        have = np.minimum(self.counts[buckets], self.depth).astype(np.int64)       # entries really held
+        add = np.minimum(ht.counts[buckets], ht.depth).astype(np.int64)
+        fits = have + add <= self.depth
+        fb, fh, fa = buckets[fits], have[fits], add[fits]
+        for j in range(int(fa.max(initial=0))):                # slot j of the incoming rows, all buckets at once
+            m = fa > j
+            self.table[fb[m], fh[m] + j] = ht.table[fb[m], j] + shift
+        self.counts[fb] = fh + fa
+        for b, h, a in zip(buckets[~fits], have[~fits], add[~fits]):
+            pool = np.concatenate([self.table[b, :h], ht.table[b, :a] + shift])
+            self.table[b] = np.random.permutation(pool)[:self.depth]
+            self.counts[b] += ht.counts[b]
         self._touch()
 
     def name_to_id(self, name, add_if_missing=False):
-        """Name -> id, optionally allocating (hash_table.py:325-345)."""
-        if isinstance(name, (str, bytes)):
-            if name not in self.names:
-                if not add_if_missing:
-                    raise ValueError("name " + str(name) + " not found")
-                try:
-                    id_ = self.names.index(None)
-                    self.names[id_] = name
-                    self.hashesperid[id_] = 0
-                except ValueError:
-                    self.names.append(name)
-                    self.hashesperid = np.append(self.hashesperid, [0]).astype(np.uint32)
-            id_ = self.names.index(name)
-        else:
-            id_ = name
-        return id_
+        """Name -> id (an int is passed through); with add_if_missing a new name takes the first
+        freed slot, else the end of the list (hash_table.py:325-345)."""
+        if not isinstance(name, (str, bytes)):
+            return name
+        if name in self.names:
+            return self.names.index(name)
+        if not add_if_missing:
+            raise ValueError("name " + str(name) + " not found")
+        if None in self.names:
+            slot = self.names.index(None)
+            self.names[slot] = name
+            self.hashesperid[slot] = 0
+            return slot
+        self.names.append(name)
+        self.hashesperid = np.append(self.hashesperid, [0]).astype(np.uint32)
+        return len(self.names) - 1
 
     def remove(self, name):
         """Drop every entry of `name` (hash_table.py:347-367)."""
@@ -220,12 +220,11 @@ class HashTable(object):
         return out
 
     def list(self, print_fn=None):
-        """Print every known item (hash_table.py:387-391)."""
-        if not print_fn:
-            print_fn = print
-        for name, count in zip(self.names, self.hashesperid):
-            if name:
-                print_fn(name + " (" + str(count) + " hashes)")
+        """One "<name> (<n> hashes)" line per stored track (hash_table.py:387-391)."""
+        emit = print_fn or print
+        for track, nhashes in zip(self.names, self.hashesperid):
+            if track:
+                emit("%s (%s hashes)" % (track, nhashes))
 
     def totalhashes(self):
         return np.sum(self.counts)

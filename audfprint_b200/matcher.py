@@ -26,20 +26,15 @@ from . import _lib
 class Matcher(object):
     """Provide matching for audfprint fingerprint queries to hash table."""
 
+    # attribute -> default, as set by audfprint_match.py:96-122
+    _REFERENCE_DEFAULTS = dict(window=1, threshcount=5, max_returns=1, search_depth=100,
+                               sort_by_time=False, verbose=False, illustrate=False, exact_count=False,
+                               find_time_range=False, time_quantile=0.02, illustrate_hpf=False,
+                               max_alignments_per_id=100)
+
     def __init__(self):
-        # defaults of audfprint_match.py:96-122
-        self.window = 1
-        self.threshcount = 5
-        self.max_returns = 1
-        self.search_depth = 100
-        self.sort_by_time = False
-        self.verbose = False
-        self.illustrate = False
-        self.exact_count = False
-        self.find_time_range = False
-        self.time_quantile = 0.02
-        self.illustrate_hpf = False
-        self.max_alignments_per_id = 100
+        for attr, default in self._REFERENCE_DEFAULTS.items():
+            setattr(self, attr, default)
 
     def _params(self):
         if self.illustrate:
@@ -224,38 +219,32 @@ class Matcher(object):
         return rows[(-rows[:, 1]).argsort(), ], pairs
 
     def match_file(self, analyzer, ht, filename, number=None):
-        """Read, fingerprint and match one file (audfprint_match.py:354-379)."""
-        q_hashes = analyzer.wavfile2hashes(filename)
-        if len(q_hashes) == 0:
-            durd = 0.0
-        else:
-            durd = analyzer.n_hop * q_hashes[-1][0] / analyzer.target_sr
+        """Read, fingerprint and match one file -> (rows[:max_returns], duration in s, #hashes)
+        (audfprint_match.py:354-379)."""
+        query = analyzer.wavfile2hashes(filename)
+        nhashes = len(query)
+        seconds = analyzer.n_hop * query[-1][0] / analyzer.target_sr if nhashes else 0.0
         if self.verbose:
-            numberstring = "#%d" % number if number is not None else ""
-            print(time.ctime(), "Analyzed", numberstring, filename, "of", ('%.3f' % durd), "s "
-                  "to", len(q_hashes), "hashes")
-        rslts = self.match_hashes(ht, q_hashes)
+            tag = "#%d" % number if number is not None else ""
+            print(time.ctime(), "Analyzed", tag, filename, "of", ('%.3f' % seconds), "s "
+                  "to", nhashes, "hashes")
+        rows = self.match_hashes(ht, query)
         if self.sort_by_time:
-            rslts = rslts[(-rslts[:, 2]).argsort(), :]
-        return rslts[:self.max_returns, :], durd, len(q_hashes)
+            rows = rows[(-rows[:, 2]).argsort(), :]
+        return rows[:self.max_returns, :], seconds, nhashes
 
     def file_match_to_msgs(self, analyzer, ht, qry, number=None):
         """Match one file and format the reference's report lines
         (audfprint_match.py:381-420)."""
-        rslts, dur, nhash = self.match_file(analyzer, ht, qry, number)
-        t_hop = analyzer.n_hop / analyzer.target_sr
-        qrymsg = qry + (' %.1f ' % dur) + "sec " + str(nhash) + " raw hashes" if self.verbose else qry
-        msgrslt = []
-        if len(rslts) == 0:
-            msgrslt.append("NOMATCH " + qrymsg if self.verbose else qrymsg + "\t")
-        else:
-            for (tophitid, nhashaligned, aligntime, nhashraw, rank, min_time, max_time) in rslts:
-                if self.verbose:
-                    msg = "Matched {:s} as {:s} at {:6.1f} s".format(qrymsg, ht.names[tophitid],
-                                                                    aligntime * t_hop)
-                    msg += (" with {:5d} of {:5d} common hashes at rank {:2d}").format(
-                        nhashaligned, nhashraw, rank)
-                    msgrslt.append(msg)
-                else:
-                    msgrslt.append(qrymsg + "\t" + ht.names[tophitid])
-        return msgrslt
+        rows, seconds, nhashes = self.match_file(analyzer, ht, qry, number)
+        frame_s = analyzer.n_hop / analyzer.target_sr
+        head = qry
+        if self.verbose:
+            head += (' %.1f ' % seconds) + "sec " + str(nhashes) + " raw hashes"
+        if len(rows) == 0:
+            return ["NOMATCH " + head if self.verbose else head + "\t"]
+        if not self.verbose:
+            return [head + "\t" + ht.names[row[0]] for row in rows]
+        return ["Matched {:s} as {:s} at {:6.1f} s".format(head, ht.names[row[0]], row[2] * frame_s)
+                + " with {:5d} of {:5d} common hashes at rank {:2d}".format(row[1], row[3], row[4])
+                for row in rows]

@@ -66,3 +66,9 @@ def db_query(j: int, noise_sigma: float = 0.01):
     trk = (j * 3) % DB_NTRACKS
     pcm, off = synth_query(db_track(trk), j, seconds=10.0, noise_sigma=noise_sigma)
     return pcm, trk, off
+
+# host-side table bookkeeping sequence (oracle/make_golden_table_ops.py)
+TABLE_OPS_SEED = 2718
+TABLE_OPS_HASHBITS = 10
+TABLE_OPS_DEPTH = 6
+TABLE_OPS_ROWS = 600

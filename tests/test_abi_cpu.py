@@ -194,3 +194,26 @@ def test_matcher_option_postprocessing_host_logic(golden_match, golden_options, 
                     rows = m.match_batch(_HT(), [q])[0]
                     assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1])
     assert nexact > 15
+
+
+def test_table_bookkeeping_equals_the_reference(golden_match, capsys):
+    """store / merge (np.random reservoir) / remove / id-slot reuse / retrieve / list: the mirror
+    class replays the scripted sequence of oracle/make_golden_table_ops.py and must reproduce the
+    live reference's table after every step."""
+    from oracle.make_golden_table_ops_replay import run
+    from tests.conftest import GOLDEN
+    want = np.load(os.path.join(GOLDEN, "table_ops.npz"))
+    seen = []
+
+    def record(tag, ht):
+        seen.append(tag)
+        assert np.array_equal(ht.table, want[tag + "/table"]), tag
+        assert np.array_equal(ht.counts, want[tag + "/counts"]), tag
+        assert np.array_equal(ht.hashesperid, want[tag + "/hashesperid"]), tag
+        assert ["" if n is None else n for n in ht.names] == want[tag + "/names"].tolist(), tag
+    ht, r9, rlate, lines = run(HashTable, golden_match, record)
+    assert seen == ["a", "b", "merged", "removed", "reused"]
+    assert np.array_equal(r9, want["retrieve_track9"]) and r9.dtype == np.int32
+    assert np.array_equal(rlate, want["retrieve_late"])
+    assert lines == want["list_lines"].tolist()
+    assert ht.names[3] == "late" and "Removed track3 ( 335 hashes)." in capsys.readouterr().out
