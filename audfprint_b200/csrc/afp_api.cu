@@ -1,6 +1,5 @@
 // C ABI of libafp.so (see include/afp.h): context, analyzer configuration and
 // the fingerprint batch driver.  Table / match entry points are in afp_match.cu.
-#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 
@@ -31,10 +30,8 @@ int afp_create(afp_ctx** out, int device) {
   }
   c->own_stream = true;
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
-  if (const char* v = getenv("AFP_K1_VARIANT")) c->k1_variant = atoi(v);
-  // double2 tables: tw256[p][r] = W256^(r p); W512^k (k < 256); log table (c_i, -0.5 log c_i)
-  // then the K1 v2 twiddles: tw1[k1][t] = W256^(t k1) (8 x 32), tw2[c][k2] = W32^(c k2) (4 x 8)
-  std::vector<double> tw(2 * (256 + 256 + 128 + 256 + 32));
+  // double2 tables: tw256[p][r] = W256^(r p); W512^k (k < 256); log table (c_i, -0.5 log c_i) x 8 copies
+  std::vector<double> tw(2 * (256 + 256 + 64 * 8));
   const long double pi = 3.14159265358979323846264338327950288L;
   for (int p = 0; p < 16; ++p)
     for (int r = 0; r < 16; ++r) {
@@ -46,23 +43,13 @@ int afp_create(afp_ctx** out, int device) {
     tw[512 + 2 * k] = (double)cosl(2.0L * pi * k / 512.0L);
     tw[512 + 2 * k + 1] = (double)(-sinl(2.0L * pi * k / 512.0L));
   }
-  for (int i = 0; i < 128; ++i) {
-    const double ci = (double)(1.0L / (1.0L + (i + 0.5L) / 128.0L));
-    tw[1024 + 2 * i] = ci;
-    tw[1024 + 2 * i + 1] = (double)(-0.5L * logl((long double)ci));
+  for (int i = 0; i < 64; ++i) {   // 8 interleaved copies: entry i of copy j at [i * 8 + j]
+    const double ci = (double)(1.0L / (1.0L + (i + 0.5L) / 64.0L));
+    for (int j = 0; j < 8; ++j) {
+      tw[1024 + 2 * (i * 8 + j)] = ci;
+      tw[1024 + 2 * (i * 8 + j) + 1] = (double)(-0.5L * logl((long double)ci));
+    }
   }
-  for (int k1 = 0; k1 < 8; ++k1)
-    for (int t = 0; t < 32; ++t) {
-      const int e = (t * k1) & 255;
-      tw[1280 + 2 * (k1 * 32 + t)] = (double)cosl(2.0L * pi * e / 256.0L);
-      tw[1280 + 2 * (k1 * 32 + t) + 1] = (double)(-sinl(2.0L * pi * e / 256.0L));
-    }
-  for (int cc = 0; cc < 4; ++cc)
-    for (int k2 = 0; k2 < 8; ++k2) {
-      const int e = (cc * k2) & 31;
-      tw[1792 + 2 * (cc * 8 + k2)] = (double)cosl(2.0L * pi * e / 32.0L);
-      tw[1792 + 2 * (cc * 8 + k2) + 1] = (double)(-sinl(2.0L * pi * e / 32.0L));
-    }
   std::vector<float> twf(2 * 512);
   for (size_t i = 0; i < twf.size(); ++i) twf[i] = (float)tw[i];
   if (c->d_twid.reserve(tw.size() * sizeof(double)) != cudaSuccess ||

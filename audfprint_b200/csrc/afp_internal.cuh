@@ -83,8 +83,7 @@ struct afp_ctx {
   DevBuf d_gauss;    // AFP_GAUSS_N doubles
   DevBuf d_window_f; // float copies for the FP32 spectrogram mode
   DevBuf d_twid_f;   // float2: tw256[p][r] (256), W512^k (256)
-  DevBuf d_twid;     // double2 tables: tw256[p][r] (256), W512^k (256), log table (128), v2 tw1 (256), tw2 (32)
-  int k1_variant = 1;  // FP64 K1: 1 = 16 threads/frame, radix 16 x 16; 2 = warp/frame, 8 x 8 x 4 (AFP_K1_VARIANT)
+  DevBuf d_twid;     // double2 tables: tw256[p][r] (256), W512^k (256), log table (64 entries x 8 copies)
 
   // batch state (valid after afp_fingerprint_batch)
   int32_t nfiles = 0, nitems = 0;

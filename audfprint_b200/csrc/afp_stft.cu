@@ -33,7 +33,10 @@ constexpr int FT = AFP_FRAMES_PER_TILE;   // 16 frames per tile
 constexpr int XS = 17;                    // padded row stride of the 16x16 exchange
 constexpr int XF = 16 * XS;               // 272 doubles per frame per component
 constexpr int K1_THREADS = 256;
-constexpr int LOGTAB = 128;               // log table entries (7 mantissa bits)
+constexpr int LOGTAB = 64;                // log table entries (6 mantissa bits) ...
+constexpr int LOGCOPIES = 8;              // ... each stored 8 times, copy j in the 16-byte bank group j:
+                                          // lane (l & 7) reads copy (l & 7), so the random lookups of a
+                                          // quarter-warp never collide (4 wavefronts per LDS.128, always)
 
 struct StftArgs {
   const void* pcm;
@@ -44,9 +47,7 @@ struct StftArgs {
   const double* window;   // 512 (pre-scaled by 2^-15 for int16 PCM)
   const double2* tw256;   // [p][r] = W256^(r*p), (cos, -sin)
   const double2* w512;    // 256: (cos, -sin)(2 pi k / 512)
-  const double2* logtab;  // 128: (c_i, -0.5*log(c_i))
-  const double2* tw1;     // v2: [k1][t] = W256^(t*k1)
-  const double2* tw2;     // v2: [c][k2] = W32^(c*k2)
+  const double2* logtab;  // [64][8]: (c_i, -0.5*log(c_i)), 8 identical copies interleaved
   double* logs;           // [frames][256]
   double* nyq;            // [frames]
   double* tile_stats;     // [tiles][3]
@@ -78,7 +79,7 @@ __device__ __forceinline__ double int_to_double(int x) {
 }
 
 // 0.5*log(0.25*v) for v > 0 normal; table-driven, |abs error| ~ 1e-16 + 0.5 ulp.
-//   v = 2^e * m, m in [1,2); i = top 7 mantissa bits; r = m*c_i - 1, |r| <= 2^-8
+//   v = 2^e * m, m in [1,2); i = top 6 mantissa bits; r = m*c_i - 1, |r| <= 2^-7
 //   0.5*log(v/4) = (e-2)*ln2/2 + t_i + 0.5*log1p(r),  t_i = -0.5*log(c_i)
 // Inputs that are 0 / denormal / inf / nan give a meaningless value here; the
 // caller detects them with is_special() and patches with half_log_quarter_slow().
@@ -87,13 +88,15 @@ __device__ __forceinline__ bool is_special(double v) {
   return (unsigned)(__double2hiint(v) - 0x00100000) >= 0x7fe00000u;
 }
 
-__device__ __forceinline__ double half_log_quarter(double v, const double2* s_logtab) {
+// s_logtab_lane = table base + (lane & 7): this lane's private copy (stride LOGCOPIES).
+__device__ __forceinline__ double half_log_quarter(double v, const double2* s_logtab_lane) {
   const int hi = __double2hiint(v);
   const int lo = __double2loint(v);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const double2 ct = s_logtab[(hi >> 13) & (LOGTAB - 1)];
+  const double2 ct = s_logtab_lane[((hi >> 14) & (LOGTAB - 1)) * LOGCOPIES];
   const double r = fma(m, ct.x, -1.0);
-  double p = -0.5 / 6.0;
+  double p = 0.5 / 7.0;
+  p = fma(p, r, -0.5 / 6.0);
   p = fma(p, r, 0.5 / 5.0);
   p = fma(p, r, -0.5 / 4.0);
   p = fma(p, r, 0.5 / 3.0);
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
   double* s_win = reinterpret_cast<double*>(smem_raw);                 // 512
   double2* s_tw256 = reinterpret_cast<double2*>(s_win + 512);          // 256, [p][r]
   double2* s_w512 = s_tw256 + 256;                                     // 256
-  double2* s_logtab = s_w512 + 256;                                    // 128
-  double* s_xr = reinterpret_cast<double*>(s_logtab + LOGTAB);         // FT * XF
+  double2* s_logtab_all = s_w512 + 256;                                // LOGTAB * LOGCOPIES
+  double* s_xr = reinterpret_cast<double*>(s_logtab_all + LOGTAB * LOGCOPIES);   // FT * XF
   double* s_xi = s_xr + FT * XF;                                       // FT * XF
   double* s_red = s_xi + FT * XF;                                      // 3 * 8
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_red + 24);   // 2
@@ -208,12 +211,13 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
     s_tw256[i] = a.tw256[i];
     s_w512[i] = a.w512[i];
   }
-  for (int i = tid; i < LOGTAB; i += K1_THREADS) s_logtab[i] = a.logtab[i];
+  for (int i = tid; i < LOGTAB * LOGCOPIES; i += K1_THREADS) s_logtab_all[i] = a.logtab[i];
   __syncthreads();
 
   const int g = tid >> 4;   // frame within the tile
   const int r = tid & 15;   // cooperating thread within the frame
   const int lane = tid & 31;
+  const double2* s_logtab = s_logtab_all + (lane & (LOGCOPIES - 1));   // this lane's copy of the log table
   const int src_lane = (lane & 16) | ((16 - r) & 15);
   uint32_t phases = 0u;   // bit b = parity to wait for on barrier b
 
@@ -357,172 +361,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
       double m = 0.0, mn = INFINITY, sm = 0.0;
 #pragma unroll
       for (int w = 0; w < K1_THREADS / 32; ++w) {
-        m = fmax(m, s_red[w * 3 + 0]);
-        mn = fmin(mn, s_red[w * 3 + 1]);
-        sm += s_red[w * 3 + 2];
-      }
-      a.tile_stats[(size_t)tile * 3 + 0] = 0.25 * m;
-      a.tile_stats[(size_t)tile * 3 + 1] = mn;
-      a.tile_stats[(size_t)tile * 3 + 2] = sm;
-    }
-    if (NBUF == 2) buf ^= 1;
-    cur = nxt;
-    if (tile + 2 * G < a.tile_end) nxt = make_tile<PcmT>(a, desc_nn, tile + 2 * G);
-    item_nn = item_n3;
-    if (NBUF == 1 && next < a.tile_end) stage_tile<PcmT>(a, cur, s_pcm, s_bar);
-  }
-}
-
-
-// ---- K1 v2: one WARP per frame, 256-point FFT as 8 x 8 x 4 (afp_fft.cuh) --------------------
-// Same tiles, PCM ring, statistics and outputs as afp_stft_kernel; what changes is the work
-// split inside a tile: warp w transforms frames w and w + 8, each lane holding 8 complex points
-// instead of 16.  ~half the registers and 40 % less exchange memory per CTA -> three CTAs
-// (24 warps) per SM instead of two (16), at the price of a second shared-memory exchange.
-struct V2Emit {
-  double* out;          // logs + frame * 256
-  double* nyq;          // &nyq[frame]
-  double* mag;          // mag + frame * 257 or nullptr
-  const double2* s_logtab;
-  double vmax, vsum;
-  int hmin;
-  __device__ __forceinline__ void operator()(int k, double ss) {
-    double lg = half_log_quarter(ss, s_logtab);
-    if (is_special(ss)) lg = half_log_quarter_slow(ss);   // digital silence etc.: rare
-    if (k < AFP_NBINS) out[k] = lg; else *nyq = lg;
-    if (mag) mag[k] = sqrt(0.25 * ss);
-    vmax = fmax(vmax, ss);
-    hmin = min(hmin, __double2hiint(ss));
-    vsum += lg;
-  }
-};
-
-constexpr size_t k1_v2_smem_bytes(size_t pcm_elem, int nbuf) {
-  return 512 * 8 + (256 + 32 + 256 + LOGTAB) * 16 + (size_t)(K1_THREADS / 32) * 2 * AFP_V2_XN * 8 + 24 * 8 + 16 +
-         nbuf * (FT + 1) * 256 * pcm_elem;
-}
-
-template <typename PcmT, bool WRITE_MAG>
-__global__ void __launch_bounds__(K1_THREADS, 3) afp_stft_v2_kernel(StftArgs a) {
-  constexpr int NBUF = PcmTraits<PcmT>::NBUF;
-  constexpr int NW = K1_THREADS / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_win = reinterpret_cast<double*>(smem_raw);                 // 512
-  double2* s_tw1 = reinterpret_cast<double2*>(s_win + 512);            // 256
-  double2* s_tw2 = s_tw1 + 256;                                        // 32
-  double2* s_w512 = s_tw2 + 32;                                        // 256
-  double2* s_logtab = s_w512 + 256;                                    // 128
-  double* s_x = reinterpret_cast<double*>(s_logtab + LOGTAB);          // NW * 2 * AFP_V2_XN
-  double* s_red = s_x + NW * 2 * AFP_V2_XN;                            // 3 * NW
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_red + 24);   // 2
-  PcmT* s_pcm = reinterpret_cast<PcmT*>(s_bar + 2);                    // NBUF * (FT+1)*256, 16 B aligned
-  constexpr int PCM_BUF = (FT + 1) * AFP_N_HOP;
-
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar + 1)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < 512; i += K1_THREADS) s_win[i] = a.window[i];
-  for (int i = tid; i < 256; i += K1_THREADS) {
-    s_tw1[i] = a.tw1[i];
-    s_w512[i] = a.w512[i];
-  }
-  if (tid < 32) s_tw2[tid] = a.tw2[tid];
-  for (int i = tid; i < LOGTAB; i += K1_THREADS) s_logtab[i] = a.logtab[i];
-  __syncthreads();
-
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  double* xr = s_x + warp * 2 * AFP_V2_XN;
-  double* xi = xr + AFP_V2_XN;
-  const int src_lane = afp_v2_partner_lane(lane & 7, lane >> 3);
-  uint32_t phases = 0u;
-
-  int tile = a.tile_begin + blockIdx.x;
-  if (tile >= a.tile_end) return;
-  const int G = gridDim.x;
-  TileInfo cur = make_tile<PcmT>(a, a.items[a.tile_item[tile]], tile);
-  TileInfo nxt = cur;
-  if (tile + G < a.tile_end) nxt = make_tile<PcmT>(a, a.items[a.tile_item[tile + G]], tile + G);
-  int item_nn = (tile + 2 * G < a.tile_end) ? a.tile_item[tile + 2 * G] : 0;
-  stage_tile<PcmT>(a, cur, s_pcm, s_bar);
-  int buf = 0;
-
-  for (; tile < a.tile_end; tile += G) {
-    const int next = tile + G;
-    if (NBUF == 2 && next < a.tile_end) stage_tile<PcmT>(a, nxt, s_pcm + (buf ^ 1) * PCM_BUF, s_bar + (buf ^ 1));
-    ItemDesc desc_nn = a.items[item_nn];
-    const int item_n3 = (tile + 3 * G < a.tile_end) ? a.tile_item[tile + 3 * G] : 0;
-    if (cur.tma) {
-      wait_bar(s_bar + buf, (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-    } else {
-      __syncthreads();
-    }
-
-    V2Emit em;
-    em.s_logtab = s_logtab;
-    em.vmax = 0.0;
-    em.vsum = 0.0;
-    em.hmin = 0x7ff00000;
-#pragma unroll 1
-    for (int g = warp; g < cur.nft; g += NW) {   // warp-uniform: whole warps work on a frame
-      const int64_t frame = cur.frame0 + g;
-      em.out = a.logs + frame * AFP_NBINS;
-      em.nyq = a.nyq + frame;
-      em.mag = WRITE_MAG ? a.mag + frame * 257 : nullptr;
-      double zr[8], zi[8];
-      {
-        const PcmT* fr = s_pcm + buf * PCM_BUF + g * AFP_N_HOP;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i0 = 2 * (32 * q + lane);
-          const double2 w = *reinterpret_cast<const double2*>(s_win + i0);
-          double x0, x1;
-          PcmTraits<PcmT>::load2(fr + i0, x0, x1);
-          zr[q] = x0 * w.x;
-          zi[q] = x1 * w.y;
-        }
-      }
-      afp_v2_stage_a<double, double2>(lane, zr, zi, s_tw1, xr, xi);
-      __syncwarp();
-      afp_v2_stage_b<double, double2>(lane, zr, zi, s_tw2, xr, xi);
-      __syncwarp();
-      afp_v2_store_b<double>(lane, zr, zi, xr, xi);
-      __syncwarp();
-      double zar[4], zai[4], zbr[4], zbi[4], pr[4], pi[4];
-      afp_v2_stage_c<double>(lane, zar, zai, zbr, zbi, xr, xi);
-      __syncwarp();   // the next frame's stage A may overwrite the buffer
-#pragma unroll
-      for (int k3 = 0; k3 < 4; ++k3) {
-        pr[k3] = __shfl_sync(0xffffffffu, zbr[3 - k3], src_lane);
-        pi[k3] = __shfl_sync(0xffffffffu, zbi[3 - k3], src_lane);
-      }
-      afp_v2_pairs<double, double2, V2Emit>(lane, zar, zai, zbr, zbi, pr, pi, s_w512, em);
-    }
-    // deterministic CTA reduction of (max |S|^2, lower bound of min log, sum log)
-    int hmin = __reduce_min_sync(0xffffffffu, em.hmin);
-    const double v_lo = __hiloint2double(hmin, 0);
-    double vmin = hmin >= 0x7ff00000 ? INFINITY
-                  : (hmin < 0x00100000 ? -INFINITY : half_log_quarter(v_lo, s_logtab));
-    double vmax = em.vmax, vsum = em.vsum;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-    }
-    if (lane == 0) {
-      s_red[warp * 3 + 0] = vmax;
-      s_red[warp * 3 + 1] = vmin;
-      s_red[warp * 3 + 2] = vsum;
-    }
-    __syncthreads();   // also: every thread is done with s_pcm[buf]
-    if (tid == 0) {
-      double m = 0.0, mn = INFINITY, sm = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
         m = fmax(m, s_red[w * 3 + 0]);
         mn = fmin(mn, s_red[w * 3 + 1]);
         sm += s_red[w * 3 + 2];
@@ -741,7 +579,8 @@ __global__ void afp_tile_table_kernel(const ItemDesc* items, int nitems, int32_t
 }
 
 constexpr size_t k1_smem_bytes(size_t pcm_elem, int nbuf) {
-  return 512 * 8 + 256 * 16 * 2 + LOGTAB * 16 + 2 * FT * XF * 8 + 24 * 8 + 16 + nbuf * (FT + 1) * 256 * pcm_elem;
+  return 512 * 8 + 256 * 16 * 2 + LOGTAB * LOGCOPIES * 16 + 2 * FT * XF * 8 + 24 * 8 + 16 +
+         nbuf * (FT + 1) * 256 * pcm_elem;
 }
 
 // ---- per-item statistics: floor, mean (audfprint_analyze.py:283-286) ----------
@@ -860,8 +699,6 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
   a.tw256 = c->d_twid.as<double2>();
   a.w512 = c->d_twid.as<double2>() + 256;
   a.logtab = c->d_twid.as<double2>() + 512;
-  a.tw1 = c->d_twid.as<double2>() + 640;
-  a.tw2 = c->d_twid.as<double2>() + 896;
   a.logs = c->d_logs.as<double>();
   a.nyq = c->d_nyq.as<double>();
   a.tile_stats = c->d_tile_stats.as<double>();
@@ -871,8 +708,7 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
   a.w512_f = c->d_twid_f.as<float2>() + 256;
   a.logs_f = c->d_logs.as<float>();
   const bool f32 = c->ap.spectrogram_fp32 != 0;
-  const bool v2 = !f32 && c->k1_variant == 2;
-  const int nctas = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * ((f32 || v2) ? 3 : 2));
+  const int nctas = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * (f32 ? 3 : 2));
   const dim3 grid((unsigned)nctas), block(K1_THREADS);
   cudaError_t e;
 #define LAUNCH_F32(T, M)                                                                              \
@@ -889,20 +725,7 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
                              (int)smem);                                                          \
     if (e == cudaSuccess) afp_stft_kernel<T, M><<<grid, block, smem, c->stream>>>(a);             \
   } while (0)
-#define LAUNCH_V2(T, M)                                                                              \
-  do {                                                                                               \
-    const size_t smem = k1_v2_smem_bytes(sizeof(T), PcmTraits<T>::NBUF);                             \
-    e = cudaFuncSetAttribute(afp_stft_v2_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)smem);                                                             \
-    if (e == cudaSuccess) afp_stft_v2_kernel<T, M><<<grid, block, smem, c->stream>>>(a);             \
-  } while (0)
-  if (v2) {
-    if (dtype == AFP_PCM_I16) {
-      if (mag_out) LAUNCH_V2(int16_t, true); else LAUNCH_V2(int16_t, false);
-    } else {
-      if (mag_out) LAUNCH_V2(float, true); else LAUNCH_V2(float, false);
-    }
-  } else if (f32) {
+  if (f32) {
     if (dtype == AFP_PCM_I16) {
       if (mag_out) LAUNCH_F32(int16_t, true); else LAUNCH_F32(int16_t, false);
     } else {
@@ -915,7 +738,6 @@ int afp_launch_stft(afp_ctx* c, const void* pcm, int dtype, double* mag_out, int
   }
 #undef LAUNCH
 #undef LAUNCH_F32
-#undef LAUNCH_V2
   AFP_CUDA(c, e);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
