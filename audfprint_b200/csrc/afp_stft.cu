@@ -130,7 +130,9 @@ struct TileInfo {
   int64_t j0;         // the same relative to the item (may be < 0)
   int64_t nsamples;   // samples of the item (reflection period)
   int nft;            // frames of the tile that exist
-  bool tma;           // interior + 16-byte aligned -> bulk copy
+  int tma;            // (first << 16) | count: samples [first, first+count) of the run come by one bulk
+                      // copy (count == 0: none); whatever else the run holds - the reflected head of a
+                      // file's first tile, the tail of its last - is staged by scalar loads
 };
 
 template <typename PcmT>
@@ -142,8 +144,14 @@ __device__ __forceinline__ TileInfo make_tile(const StftArgs& a, const ItemDesc&
   ti.j0 = (int64_t)(t0 - 1) * AFP_N_HOP;   // first sample of the run (may be < 0)
   ti.src = it.sample_start + ti.j0;
   ti.nsamples = it.nsamples;
-  const bool interior = (ti.j0 >= 0) && (ti.j0 + (ti.nft + 1) * AFP_N_HOP <= it.nsamples);
-  ti.tma = interior && ((reinterpret_cast<uintptr_t>(reinterpret_cast<const PcmT*>(a.pcm) + ti.src) & 15) == 0);
+  // the part of the run that lies inside the file, trimmed to 16-byte granules; the shared-memory
+  // buffer is 16-byte aligned, so source and destination agree iff the run itself starts on one
+  constexpr int GR = 16 / (int)sizeof(PcmT);
+  const int64_t run_n = (int64_t)(ti.nft + 1) * AFP_N_HOP;
+  const int64_t lo = ti.j0 < 0 ? -ti.j0 : 0;
+  const int64_t hi = (ti.j0 + run_n <= it.nsamples ? run_n : it.nsamples - ti.j0) & ~(int64_t)(GR - 1);
+  const bool aligned = (reinterpret_cast<uintptr_t>(reinterpret_cast<const PcmT*>(a.pcm) + ti.src) & 15) == 0;
+  ti.tma = (aligned && hi > lo) ? (int)((lo << 16) | (hi - lo)) : 0;   // lo is 0 or 256: a granule multiple
   return ti;
 }
 
@@ -153,22 +161,27 @@ __device__ __forceinline__ void stage_tile(const StftArgs& a, const TileInfo& ti
                                            unsigned long long* bar) {
   const PcmT* pcm = reinterpret_cast<const PcmT*>(a.pcm);
   const int nsamp = (ti.nft + 1) * AFP_N_HOP;
-  if (ti.tma) {
+  const int t_first = ti.tma >> 16, t_count = ti.tma & 0xffff;
+  if (t_count) {
     if (threadIdx.x == 0) {
-      const uint32_t bytes = nsamp * sizeof(PcmT);
+      const uint32_t bytes = t_count * sizeof(PcmT);
       // order earlier generic-proxy accesses of this buffer before the async-proxy write
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                    : "memory");
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(dst)),
-          "l"(pcm + ti.src), "r"(bytes), "r"(smem_u32(bar))
+              smem_u32(dst + t_first)),
+          "l"(pcm + ti.src + t_first), "r"(bytes), "r"(smem_u32(bar))
           : "memory");
     }
-  } else {
+  }
+  if (t_count != nsamp) {   // samples outside the bulk copy: [0, t_first) and [t_first + t_count, nsamp)
     const PcmT* item0 = pcm + (ti.src - ti.j0);
-    for (int i = threadIdx.x; i < nsamp; i += K1_THREADS) dst[i] = item0[reflect_index(ti.j0 + i, ti.nsamples)];
+    for (int i = threadIdx.x; i < nsamp - t_count; i += K1_THREADS) {
+      const int p = i < t_first ? i : i + t_count;
+      dst[p] = item0[reflect_index(ti.j0 + p, ti.nsamples)];
+    }
   }
 }
 
@@ -239,12 +252,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) afp_stft_kernel(StftArgs a) {
     if (NBUF == 2 && next < a.tile_end) stage_tile<PcmT>(a, nxt, s_pcm + (buf ^ 1) * PCM_BUF, s_bar + (buf ^ 1));
     ItemDesc desc_nn = a.items[item_nn];                                   // consumed at the end of the iteration
     const int item_n3 = (tile + 3 * G < a.tile_end) ? a.tile_item[tile + 3 * G] : 0;   // consumed next iteration
-    if (cur.tma) {
+    if (cur.tma & 0xffff) {
       wait_bar(s_bar + buf, (phases >> buf) & 1u);
       phases ^= 1u << buf;
-    } else {
-      __syncthreads();   // scalar-staged run is visible
     }
+    if ((cur.tma & 0xffff) != (cur.nft + 1) * AFP_N_HOP) __syncthreads();   // scalar-staged samples are visible
 
     const bool active = g < cur.nft;
     const int64_t frame = cur.frame0 + g;
@@ -445,12 +457,11 @@ __global__ void __launch_bounds__(K1_THREADS, 3) afp_stft_f32_kernel(StftArgs a)
     if (NBUF == 2 && next < a.tile_end) stage_tile<PcmT>(a, nxt, s_pcm + (buf ^ 1) * PCM_BUF, s_bar + (buf ^ 1));
     ItemDesc desc_nn = a.items[item_nn];
     const int item_n3 = (tile + 3 * G < a.tile_end) ? a.tile_item[tile + 3 * G] : 0;
-    if (cur.tma) {
+    if (cur.tma & 0xffff) {
       wait_bar(s_bar + buf, (phases >> buf) & 1u);
       phases ^= 1u << buf;
-    } else {
-      __syncthreads();
     }
+    if ((cur.tma & 0xffff) != (cur.nft + 1) * AFP_N_HOP) __syncthreads();
     const bool active = g < cur.nft;
     const int64_t frame = cur.frame0 + g;
     float vmax = 0.0f, vsum = 0.0f;
