@@ -120,3 +120,32 @@ def test_batch_merge_equals_per_query_merge(golden_match, db, nshards):
             want = orc.match_hashes(table, counts, hashbits, depth, mtb, hpi, gm[k + "/q"], window=window,
                                     threshcount=thresh, search_depth=sdepth)
             assert np.array_equal(one[np.argsort(-one[:, 1], kind="stable")], want)
+
+
+def test_packed_batch_records_equal_per_query_records(golden_match):
+    """pack_shard_batch (from the arrays afp_fetch_match_candidates / afp_fetch_match_rows return)
+    lays records out exactly like pack_shard_records (from per-query dicts)."""
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, "db")
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    window, thresh, sdepth = (int(x) for x in gm["cfg_a"])
+    recs = [shard_record(table, counts, hashbits, depth, mtb, hpi, gm[k + "/q"], 0, len(hpi) // 2,
+                         window, thresh, sdepth) for k in keys]
+    nq = len(recs)
+    cand = np.full((nq, sdepth, 3), 7.5)                       # junk beyond `entries`, as a reused device buffer has
+    cnts = np.zeros((nq, 2), np.int32)
+    rows, roff = [], np.zeros(nq + 1, np.int64)
+    for i, r in enumerate(recs):
+        k = len(r["cand"])
+        cand[i, :k] = r["cand"]
+        cnts[i] = (k, r["n_above"])
+        rows.append(np.asarray(r["rows"], np.int32).reshape(-1, 7))
+        roff[i + 1] = roff[i] + len(rows[-1])
+    got = afd.pack_shard_batch(cand, cnts, np.concatenate(rows), roff, 128)
+    assert np.array_equal(got, afd.pack_shard_records(recs, sdepth, 128))
+    back = afd.unpack_shard_records(got, sdepth, 128)
+    for a, b in zip(back, recs):
+        assert a["n_above"] == b["n_above"] and np.array_equal(a["cand"], b["cand"])
+        assert np.array_equal(a["rows"], np.asarray(b["rows"], np.int32).reshape(-1, 7))
+    with pytest.raises(ValueError):
+        afd.pack_shard_batch(cand, cnts, np.concatenate(rows), roff, 1)
