@@ -251,13 +251,44 @@ class HashTable(object):
     def load(self, name):
         ext = os.path.splitext(name)[1]
         if ext == '.mat':
-            raise NotImplementedError("Matlab .mat databases (hash_table.py:248-285) are not supported")
-        self.load_pkl(name)
+            self.load_matlab(name)
+        else:
+            self.load_pkl(name)
         nhashes = int(np.sum(self.counts))
         dropped = nhashes - int(np.sum(np.minimum(self.depth, self.counts)))
         print("Read fprints for", sum(n is not None for n in self.names),
               "files (", nhashes, "hashes) from", name,
               "(%.2f%% dropped)" % (100.0 * dropped / max(1, nhashes)))
+
+    def load_matlab(self, name):
+        """Database written by the Matlab audfprint (hash_table.py:248-285): struct HT_params
+        (nhashes, depth, maxtime, hoptime, targetsr, nojenkins, ..., version last), HashTable stored
+        depth x buckets, counts, a cell array of names (empty cell = removed track) and the per-track
+        hash counts.  Matlab's 1-based ids are what the Python table stores as id + 1, so the entries
+        are taken as they are."""
+        import scipy.io
+        mat = scipy.io.loadmat(name)
+        fields = mat['HT_params'][0][0]
+
+        def scalar(k):
+            return fields[k][0][0]
+        version = scalar(-1)
+        if version < 0.9:
+            raise AssertionError("Matlab database version %s is older than 0.9" % version)
+        if not scalar(5):
+            raise AssertionError("Jenkins-hashed Matlab databases are not supported")
+        self.hashbits = _bitsfor(scalar(0))
+        self.depth = int(scalar(1))
+        self.maxtimebits = _bitsfor(scalar(2))
+        self.table = np.ascontiguousarray(mat['HashTable'].T, dtype=np.uint32)
+        self.counts = np.ascontiguousarray(mat['HashTableCounts'][0], dtype=np.int32)
+        self.names = [str(cell[0]) if len(cell) > 0 else [] for cell in mat['HashTableNames'][0]]
+        self.hashesperid = np.array(mat['HashTableLengths'][0]).astype(np.uint32)
+        self.params = {'mat_version': version, 'hoptime': scalar(3), 'targetsr': scalar(4), 'nojenkins': scalar(5)}
+        self.ht_version = HT_VERSION
+        self.dirty = False
+        self._version = getattr(self, "_version", 0) + 1
+        self._dev_stamp = None
 
     def load_pkl(self, name, file_object=None):
         f = file_object if file_object else gzip.open(name, 'rb')

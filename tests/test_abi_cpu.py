@@ -236,3 +236,18 @@ def test_wav_reader_downmixes_and_resamples(tmp_path):
     assert abs(np.argmax(spec) * 11025 / 8192 - f0) < 2.0 and abs(np.max(np.abs(d[500:-500])) - 0.5) < 0.01
     d2, sr2 = an_mod._wav_reader(fn)                      # no target rate: native rate, still mono
     assert sr2 == fs and len(d2) == len(left)
+
+
+def test_loads_matlab_database_like_the_reference():
+    """tests/golden/matlab_db.mat (oracle/make_golden_mat.py) -> the attributes the live reference's
+    loader produced for the same file."""
+    from tests.conftest import GOLDEN
+    ht = HashTable(os.path.join(GOLDEN, "matlab_db.mat"))
+    want = np.load(os.path.join(GOLDEN, "matlab_db_arrays.npz"))
+    assert np.array_equal(ht.table, want["table"]) and np.array_equal(ht.counts, want["counts"])
+    assert np.array_equal(ht.hashesperid, want["hashesperid"])
+    assert [n if isinstance(n, str) else "" for n in ht.names] == want["names"].tolist()
+    assert [ht.hashbits, ht.depth, ht.maxtimebits] == want["geometry"].tolist() and isinstance(ht.depth, int)
+    got = [ht.params[k] for k in ("mat_version", "hoptime", "targetsr", "nojenkins")]
+    assert np.allclose(got, want["params"]) and not ht.dirty
+    assert ht.table.dtype == np.uint32 and ht.table.flags["C_CONTIGUOUS"] and ht.counts.dtype == np.int32
