@@ -409,3 +409,22 @@ def peaks_save(peakfilename, peaks):
 
 def peaks_load(peakfilename):
     return _pairs_load(peakfilename, PEAK_MAGIC, 'peak')
+
+
+def glob2hashtable(pattern, density=20.0):
+    """Build a hash table from the files matching a glob pattern (audfprint_analyze.py:560-579):
+    the files are read on the host, fingerprinted in one batched device call and inserted in
+    glob order."""
+    import glob
+    import time
+    from .hash_table import HashTable
+    analyzer = Analyzer(density=density)
+    ht = HashTable()
+    files = glob.glob(pattern)
+    t0 = time.time()
+    signals = [analyzer._read(fn)[0] for fn in files]
+    counts = analyzer.ingest_batch(ht, files, signals)
+    total = analyzer.soundfiletotaldur
+    if total > 0:
+        print("Added", sum(counts), "(", sum(counts) / total, "hashes/sec) at ", (time.time() - t0) / total, "x RT")
+    return ht

@@ -146,6 +146,12 @@ class HashTable(object):
         self.hashesperid[id_] += n
         self._touch()
 
+    def get_entry(self, hash_):
+        """int32 (n,2) [id, time] rows stored under one hash, from the host arrays
+        (hash_table.py:140-148; the reference's own version trips over a misspelt attribute)."""
+        vals = self.table[hash_, :min(self.depth, int(self.counts[hash_]))].astype(np.int64)
+        return np.stack([(vals >> self.maxtimebits) - 1, vals & ((1 << self.maxtimebits) - 1)], axis=1).astype(np.int32)
+
     def merge(self, ht):
         """Append another table's tracks after ours (hash_table.py:291-323): its ids move up by
         len(self.names); a bucket that still fits keeps every entry (ours first), a bucket that
