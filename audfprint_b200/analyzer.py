@@ -275,8 +275,21 @@ class Analyzer(object):
         return [tuple(int(v) for v in r) for r in out]
 
     def spreadpeaksinvector(self, vector, width=4.0):
-        raise NotImplementedError("spreadpeaksinvector is fused into the peak kernel (afp_peaks.cu); "
-                                  "it is not exposed as a separate call")
+        """Blurred copy of `vector`: every local maximum spread by a Gaussian of SD `width`, max
+        over the bumps (audfprint_analyze.py:153-160 over spreadpeaks :162-197).  The product
+        path fuses this into the peak kernel (afp_peaks.cu `spread`); this entry point runs the
+        same arithmetic on the device for a stand-alone vector (afp_spread_peaks)."""
+        v = np.ascontiguousarray(vector, dtype=np.float64).ravel()
+        n = len(v)
+        out = np.zeros(n, np.float64)
+        if n == 0:
+            return out
+        ctx = _lib.context(self.device)
+        # the very doubles the reference caches in __sp_vals (:187-192)
+        tab = np.ascontiguousarray(np.exp(-0.5 * ((np.arange(-n, n + 1) / width) ** 2)), dtype=np.float64)
+        ctx.check(ctx.lib.afp_spread_peaks(ctx.h, v.ctypes.data, n, tab.ctypes.data, float(width), None,
+                                           out.ctypes.data))
+        return out
 
     def _read(self, filename):
         try:

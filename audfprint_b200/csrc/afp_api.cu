@@ -425,6 +425,16 @@ int afp_fetch_landmarks(afp_ctx* c, int32_t* rows, int rows_on_host) {
   return AFP_OK;
 }
 
+int afp_spread_peaks(afp_ctx* c, const double* vector, int32_t n, const double* table, double width,
+                     const double* base, double* out) {
+  if (!c || n < 0 || (n > 0 && (!vector || !out))) return AFP_ERR_INVALID;
+  if (n == 0) return AFP_OK;
+  if (n > 50000) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "spread_peaks: vector longer than 50000");
+  if (!table && !(width > 0.0)) AFP_FAIL(c, AFP_ERR_INVALID, "spread_peaks: width must be positive");
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  return afp_spread_peaks_impl(c, vector, n, table, width, base, out);
+}
+
 static int single_signal(afp_ctx* c, const void* pcm, int dtype, int on_host, int64_t n, double* out,
                          int out_on_host, bool want_mag) {
   if (!c) return AFP_ERR_INVALID;

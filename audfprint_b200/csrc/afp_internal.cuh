@@ -159,4 +159,6 @@ int afp_launch_hashes(afp_ctx* c);   // merge / scans (all files)
 int afp_write_hashes(afp_ctx* c);
 int afp_landmarks_from_peaks_impl(afp_ctx* c, const int32_t* rows, int64_t n, int on_host, int64_t* nlm);
 int afp_compact_peaks(afp_ctx* c, int shift);
+int afp_spread_peaks_impl(afp_ctx* c, const double* vector, int32_t n, const double* table, double width,
+                          const double* base, double* out);
 int afp_launch_scan_i32_to_i64(afp_ctx* c, const int32_t* in, int64_t* out, int64_t n);

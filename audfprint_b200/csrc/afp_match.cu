@@ -15,6 +15,7 @@
 // the reference reverses an unstable argsort, so the order of equal weighted
 // counts is implementation-defined there; here it is (weight desc, id desc).
 #include <math.h>
+#include <algorithm>
 #include "afp_internal.cuh"
 
 namespace {
@@ -25,7 +26,7 @@ constexpr int KCAP = 1024;        // candidate depth handled by the fast path (s
 constexpr int GCAP = 1024;        // radix select stops once the undecided set is this small
 constexpr int QCAP = 16384;       // query rows sorted in shared memory to merge probes of one bucket (128 KB)
 constexpr int CSEG = 32768;       // track ids counted per pass in shared memory (u32 counters, the same 128 KB)
-constexpr int SLOT_SHIFT = 21;    // per-query hit capacity (rows * depth) stays below 2^21
+constexpr int64_t HITS_MAX = (int64_t)1 << 30;   // per-query hit capacity (rows * depth): int indexing
 constexpr int HSET_BITS = 11;     // candidate hash set: 2048 entries for <= KCAP = 1024 keys
 constexpr int HSET = 1 << HSET_BITS;
 
@@ -342,7 +343,9 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
       // pass below leaves the array zeroed again)
       {
         uint4* z4 = reinterpret_cast<uint4*>(s_cnt);
-        const int nz = sorted ? n2 / 2 : 0;                      // n2 keys of 8 bytes = n2/2 uint4
+        // n2 keys of 8 bytes = n2/2 uint4, at least one (a 0- or 1-row query leaves one key); an
+        // unsorted query wrote nothing here and finds the zeros the previous harvest left
+        const int nz = sorted ? max(1, n2 / 2) : 0;
         for (int i = tid; i < nz; i += MT) z4[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       __syncthreads();
@@ -865,7 +868,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   if (h_mm[1] < 0) AFP_FAIL(c, AFP_ERR_INVALID, "negative query time");
 
   // persistent grid; a fixed CTA count keeps the scratch layout (and its zeroed state) reusable
-  const int nctas = c->num_sms;
+  int nctas = c->num_sms;
   MatchArgs a;
   a.q = dq;
   a.qoff = c->d_qoff.as<int64_t>();
@@ -885,10 +888,20 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   a.bias = h_mm[0] + p->window + 2;
   a.hist_len = (1 << c->tab.maxtimebits) + a.bias + p->window + 4;
   a.row_cap = p->row_capacity > 0 ? p->row_capacity : 256;
-  if (a.hits_cap >= ((int64_t)1 << SLOT_SHIFT) || a.nids >= ((int64_t)1 << 24))
-    AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large (rows * depth >= 2^21) or more than 2^24 track ids");
+  if (a.hits_cap >= HITS_MAX || a.nids >= ((int64_t)1 << 24))
+    AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "query too large (rows * depth >= 2^30) or more than 2^24 track ids");
   const size_t per_cta = (size_t)a.hits_cap * (sizeof(uint2) + 4 * sizeof(uint32_t) + sizeof(double)) +
                          (size_t)a.hist_len * 2 * sizeof(int32_t) + 256;
+  // The scratch is per CTA and sized for the longest query of the batch (the reference has no
+  // query-length limit, hash_table.py:150-176; whole shows are matched in searching_for_ads.md):
+  // when it would not fit the memory budget the grid shrinks instead of the call failing.
+  {
+    size_t free_b = 0, total_b = 0;
+    AFP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::max<size_t>((free_b + c->d_mscratch.cap) / 2, (size_t)1 << 30);
+    if (per_cta * (size_t)nctas > budget) nctas = (int)std::max<size_t>(1, budget / per_cta);
+    if (per_cta > budget) AFP_FAIL(c, AFP_ERR_NOMEM, "match scratch of one query exceeds the device memory budget");
+  }
   const size_t before = c->d_mscratch.cap;
   AFP_CUDA(c, c->d_mscratch.reserve(per_cta * (size_t)nctas + 1024));
   AFP_CUDA(c, c->d_mrows.reserve(sizeof(int32_t) * 7 * (size_t)a.row_cap * (size_t)nqueries));
@@ -911,7 +924,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   // the histograms are left zeroed by the kernel itself: clear them only when the
   // carve-up changed (or the buffer moved)
   const uint64_t layout = (uint64_t)a.hits_cap * 1000003ull ^ (uint64_t)a.nids * 7919ull ^ (uint64_t)a.hist_len * 31ull ^
-                          (uint64_t)(uintptr_t)c->d_mscratch.p ^ (uint64_t)before;
+                          (uint64_t)(uintptr_t)c->d_mscratch.p ^ (uint64_t)before ^ (uint64_t)nctas * 2654435761ull;
   if (layout != c->match_layout) {
     AFP_CUDA(c, cudaMemsetAsync(zero0, 0, (size_t)(base - zero0), c->stream));
     c->match_layout = layout;

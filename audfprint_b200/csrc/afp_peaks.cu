@@ -394,7 +394,60 @@ __global__ void afp_gather_npeaks_kernel(const int32_t* item_npeaks, int nfiles,
   if (f < nfiles) out[f] = item_npeaks[f * shifts + shift];
 }
 
+// Analyzer.spreadpeaksinvector / spreadpeaks as a stand-alone call (audfprint_analyze.py:153-197):
+// one CTA; the local maxima of `vec` are listed in shared memory, then every output element
+// takes the max over their scaled Gaussians (same products, same max as the reference).
+__global__ void __launch_bounds__(256) afp_spread_kernel(const double* vec, int n, const double* tab,
+                                                        const double* base, double* out) {
+  extern __shared__ int s_pk[];      // indices of the local maxima
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const bool ge = (i == 0) ? true : (vec[i] >= vec[i - 1]);          // locmax :46-48
+    const bool ge_next = (i == n - 1) ? false : (vec[i + 1] >= vec[i]);
+    if (ge && !ge_next) s_pk[atomicAdd(&s_n, 1)] = i;
+  }
+  __syncthreads();
+  const int np = s_n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = base ? base[i] : 0.0;
+    for (int k = 0; k < np; ++k) {
+      const int p = s_pk[k];
+      v = fmax(v, __dmul_rn(vec[p], tab[i + n - p]));                  // :195-196
+    }
+    out[i] = v;
+  }
+}
+
 }  // namespace
+
+int afp_spread_peaks_impl(afp_ctx* c, const double* vector, int32_t n, const double* table, double width,
+                          const double* base, double* out) {
+  const size_t nn = (size_t)n;
+  AFP_CUDA(c, c->d_tmp.reserve(sizeof(double) * (5 * nn + 8)));
+  double* d_vec = c->d_tmp.as<double>();
+  double* d_tab = d_vec + nn;             // 2n+1
+  double* d_base = d_tab + 2 * nn + 1;
+  double* d_out = d_base + nn;
+  std::vector<double> tab(2 * nn + 1);
+  for (size_t j = 0; j < tab.size(); ++j) {
+    const double u = ((double)j - (double)n) / width;
+    tab[j] = table ? table[j] : exp(-0.5 * (u * u));
+  }
+  AFP_CUDA(c, cudaMemcpyAsync(d_vec, vector, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
+  AFP_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, c->stream));
+  if (base) AFP_CUDA(c, cudaMemcpyAsync(d_base, base, sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
+  const size_t smem = sizeof(int) * nn;
+  if (smem > 48 * 1024)
+    AFP_CUDA(c, cudaFuncSetAttribute(afp_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  afp_spread_kernel<<<1, 256, smem, c->stream>>>(d_vec, n, d_tab, base ? d_base : nullptr, d_out);
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches++;
+  AFP_CUDA(c, cudaMemcpyAsync(out, d_out, sizeof(double) * nn, cudaMemcpyDeviceToHost, c->stream));
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));   // `tab` must outlive the copy
+  return AFP_OK;
+}
 
 int afp_launch_peaks(afp_ctx* c, int item0, int nitems) {
   if (nitems <= 0) return AFP_OK;

@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import gzip
 import io
+import itertools
 import math
 import os
 import pickle
@@ -27,6 +28,10 @@ from . import _lib
 HT_VERSION = 20170724
 HT_COMPAT_VERSION = 20170724
 HT_OLD_COMPAT_VERSION = 20140920
+
+
+class AfpStateError(RuntimeError):
+    pass
 
 
 def _bitsfor(maxval):
@@ -50,19 +55,36 @@ _REF_ATTRS = ("hashbits", "depth", "maxtimebits", "table", "counts", "names", "h
               "ht_version", "dirty")
 
 
-def _as_reference_object(ht):
-    """An object that pickles as `hash_table.HashTable` with the reference's attribute set.
-    If the reference module is not importable a stand-in module of that name is registered
-    for the duration of the dump (pickle stores only the class PATH, not its code)."""
-    import sys
-    import types
-    mod = sys.modules.get("hash_table")
-    cls = getattr(mod, "HashTable", None) if mod is not None else None
-    if cls is None:
+class _reference_pickle_class(object):
+    """Context manager yielding a class that pickles as `hash_table.HashTable`.
+    pickle stores only the class PATH and checks at dump time that the path resolves to the very
+    class being pickled, so a stand-in module of that name holds a stand-in class for the
+    duration of the dump; whatever `hash_table` was before (nothing, the reference's module, or
+    this module under that name - INTEGRATION.md option A) is put back afterwards."""
+    _missing = object()
+
+    def __enter__(self):
+        import sys
+        import types
         mod = types.ModuleType("hash_table")
         cls = type("HashTable", (object,), {"__module__": "hash_table"})
         mod.HashTable = cls
+        self._prev = sys.modules.get("hash_table", self._missing)
         sys.modules["hash_table"] = mod
+        return cls
+
+    def __exit__(self, *exc):
+        import sys
+        if self._prev is self._missing:
+            sys.modules.pop("hash_table", None)
+        else:
+            sys.modules["hash_table"] = self._prev
+        return False
+
+
+def _as_reference_object(ht, cls):
+    """An instance of `cls` (see _reference_pickle_class) carrying exactly the reference's
+    attribute set."""
     obj = object.__new__(cls)
     obj.__dict__.update({k: getattr(ht, k) for k in _REF_ATTRS})
     obj.__dict__["dirty"] = False
@@ -74,8 +96,7 @@ class HashTable(object):
 
     def __init__(self, filename=None, hashbits=20, depth=100, maxtime=16384, device=None):
         self.device = device
-        self._dev_stamp = None       # identity of the arrays last uploaded
-        self._version = 0            # bumped on every mutation
+        self._init_device_state()
         if filename is not None:
             self.load(filename)
             return
@@ -86,20 +107,63 @@ class HashTable(object):
         self.names, self.hashesperid = [], np.zeros(0, np.uint32)
         self.params, self.ht_version, self.dirty = {}, HT_VERSION, True
 
+    # ---- host arrays <-> device copy bookkeeping ------------------------------------
+    # `table`, `counts` and `hashesperid` are the reference's public attributes
+    # (hash_table.py:59-81).  They are properties here so that (a) REBINDING one of them
+    # (`ht.table = other`) is seen by the device copy, and (b) after a device-side
+    # `store_batch` the host arrays are refreshed from the device before anyone reads them.
+    # Writing INTO the arrays in place (`ht.table[b, s] = v`) cannot be observed: call
+    # `ht.touch()` afterwards (every mutating method of this class does).
+    _tokens = itertools.count(1)
+
+    def _init_device_state(self):
+        self._token = next(HashTable._tokens)   # process-unique: never equal to another table's
+        self._version = 0                       # bumped on every change of the host state
+        self._dev_newer = False                 # device copy holds inserts the host arrays lack
+        self._shard = None
+
+    def _bump(self):
+        self._version = getattr(self, "_version", 0) + 1
+
+    def touch(self):
+        """Tell the device copy that the host arrays were modified in place."""
+        self._bump()
+
+    def _host(self, attr):
+        if getattr(self, "_dev_newer", False):
+            self._pull_device()
+        return self.__dict__[attr]
+
+    table = property(lambda self: self._host("_table"),
+                     lambda self, a: (self.__dict__.__setitem__("_table", a), self._bump())[0])
+    counts = property(lambda self: self._host("_counts"),
+                      lambda self, a: (self.__dict__.__setitem__("_counts", a), self._bump())[0])
+    hashesperid = property(lambda self: self.__dict__["_hashesperid"],
+                           lambda self, a: (self.__dict__.__setitem__("_hashesperid", a), self._bump())[0])
+
     # ---- pickling: only plain host state travels (reference pickles the object) ----
     def __getstate__(self):
+        if getattr(self, "_dev_newer", False):
+            self._pull_device()
         st = dict(self.__dict__)
-        st.pop("_dev_stamp", None)
+        for k in ("_token", "_version", "_dev_newer", "_shard"):
+            st.pop(k, None)
+        for k in ("table", "counts", "hashesperid"):      # the reference's attribute names
+            st[k] = st.pop("_" + k)
         return st
 
     def __setstate__(self, st):
+        st = dict(st)
+        st.pop("_dev_stamp", None)
+        for k in ("table", "counts", "hashesperid"):
+            if k in st:
+                st["_" + k] = st.pop(k)
         self.__dict__.update(st)
-        self._dev_stamp = None
-        self.__dict__.setdefault("_version", 0)
         self.__dict__.setdefault("device", None)
+        self._init_device_state()
 
     def _touch(self):
-        self._version += 1
+        self._bump()
         self.dirty = True
 
     def reset(self):
@@ -244,7 +308,8 @@ class HashTable(object):
             for key in params:
                 self.params[key] = params[key]
         f = file_object if file_object else gzip.open(name, 'wb')
-        pickle.dump(_as_reference_object(self), f, pickle.HIGHEST_PROTOCOL)
+        with _reference_pickle_class() as cls:
+            pickle.dump(_as_reference_object(self, cls), f, pickle.HIGHEST_PROTOCOL)
         if not file_object:
             f.close()
         self.dirty = False
@@ -293,8 +358,8 @@ class HashTable(object):
         self.params = {'mat_version': version, 'hoptime': scalar(3), 'targetsr': scalar(4), 'nojenkins': scalar(5)}
         self.ht_version = HT_VERSION
         self.dirty = False
-        self._version = getattr(self, "_version", 0) + 1
-        self._dev_stamp = None
+        self._dev_newer = False
+        self._bump()
 
     def load_pkl(self, name, file_object=None):
         f = file_object if file_object else gzip.open(name, 'rb')
@@ -318,26 +383,29 @@ class HashTable(object):
         self.hashesperid = np.array(temp.hashesperid).astype(np.uint32)
         self.params = temp.params
         self.dirty = False
-        self._version = getattr(self, "_version", 0) + 1
-        self._dev_stamp = None
+        self._dev_newer = False
+        self._bump()
 
     # ---- device copy + probe --------------------------------------------------------
+    def _stamp(self, shard=None):
+        return (self._token, self._version, int(self.hashbits), int(self.depth), int(self.maxtimebits), shard)
+
     def _sync_device(self):
         """Upload table/counts/hashesperid if they changed since the last upload."""
         ctx = _lib.context(self.device)
-        stamp = (id(self), self._version, id(self.table), id(self.counts))
-        shard = getattr(self, "_shard", None)
-        if shard is not None and ctx.table_key == ("shard", id(self), self._version, shard[0], shard[1]):
+        if self._shard is not None and ctx.table_key == self._stamp(self._shard):
             return ctx              # device copy is this table's shard
-        if ctx.table_key != stamp:
+        if ctx.table_key != self._stamp():
             self._shard = None
             table = np.ascontiguousarray(self.table, dtype=np.uint32)
             counts = np.ascontiguousarray(self.counts, dtype=np.int32)
             hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
+            if table.shape != (1 << int(self.hashbits), int(self.depth)) or counts.shape != (1 << int(self.hashbits),):
+                raise ValueError("table/counts shapes do not match hashbits/depth")
             ctx.check(ctx.lib.afp_table_upload(ctx.h, table.ctypes.data, counts.ctypes.data, int(self.hashbits),
                                                int(self.depth), int(self.maxtimebits),
                                                hpi.ctypes.data if len(hpi) else None, len(hpi), 1))
-            ctx.table_key = stamp
+            ctx.table_key = self._stamp()
         return ctx
 
     def restrict_device_ids(self, id_lo, id_hi):
@@ -350,8 +418,12 @@ class HashTable(object):
         ctx = self._sync_device()
         ctx.check(ctx.lib.afp_table_restrict_ids(ctx.h, int(id_lo), int(id_hi)))
         self._shard = (int(id_lo), int(id_hi))
-        ctx.table_key = ("shard", id(self), self._version, int(id_lo), int(id_hi))
+        ctx.table_key = self._stamp(self._shard)
         return ctx
+
+    def _pull_device(self):
+        """Refresh the host arrays from the device copy after device-side inserts."""
+        raise AfpStateError("device copy is newer but no download path is built")
 
     def get_hits(self, hashes):
         """[time, hash] rows -> int32 (nhits,4) [id, dtime, hash, time] rows in

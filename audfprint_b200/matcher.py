@@ -245,6 +245,14 @@ class Matcher(object):
             return ["NOMATCH " + head if self.verbose else head + "\t"]
         if not self.verbose:
             return [head + "\t" + ht.names[row[0]] for row in rows]
-        return ["Matched {:s} as {:s} at {:6.1f} s".format(head, ht.names[row[0]], row[2] * frame_s)
-                + " with {:5d} of {:5d} common hashes at rank {:2d}".format(row[1], row[3], row[4])
-                for row in rows]
+        msgs = []
+        for tid, aligned, dtime, raw, rank, t_lo, t_hi in rows:
+            if self.find_time_range:
+                # -R report: matched span of the query and where it starts in the reference track
+                # (audfprint_match.py:402-407)
+                msg = "Matched {:6.1f} s starting at {:6.1f} s in {:s} to time {:6.1f} s in {:s}".format(
+                    (t_hi - t_lo) * frame_s, t_lo * frame_s, qry, (t_lo + dtime) * frame_s, ht.names[tid])
+            else:
+                msg = "Matched {:s} as {:s} at {:6.1f} s".format(head, ht.names[tid], dtime * frame_s)
+            msgs.append(msg + " with {:5d} of {:5d} common hashes at rank {:2d}".format(aligned, raw, rank))
+        return msgs

@@ -38,6 +38,35 @@ METRIC = "audio_seconds_fingerprinted_per_sec"
 UNIT = "audio-s/s"
 
 
+# ---------------------------------------------------------------- host cores
+def host_cores():
+    """Threads this process may really use: the scheduler affinity mask and the cgroup CPU quota
+    bound it, os.cpu_count() does not (a 128-thread box with an 8-CPU quota reports 128; a pool of
+    128 processes on it measured 5x below the same command on an unconstrained node)."""
+    info = {"os_cpu_count": os.cpu_count() or 1}
+    n = info["os_cpu_count"]
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+        n = min(n, info["affinity"])
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1"):
+                info["cgroup_cpus"] = float(quota) / period
+                n = min(n, max(1, int(info["cgroup_cpus"] + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    info["used"] = max(1, n)
+    return info
+
+
 # ---------------------------------------------------------------- synthetic input
 def _gen(args):
     seed, secs = args
@@ -392,7 +421,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
+    cores_info = host_cores()
+    cores = cores_info["used"]
     if a.impl != "reference":
         cores = max(2, cores // max(1, world))      # every rank forks its own generator pool
     nsamp = int(round(a.seconds * SR))

@@ -150,6 +150,16 @@ int afp_landmarks_from_peaks(afp_ctx* ctx, const int32_t* peak_rows, int64_t npe
                              int64_t* nlandmarks);
 int afp_fetch_landmarks(afp_ctx* ctx, int32_t* rows, int rows_on_host);
 
+/* Analyzer.spreadpeaksinvector (audfprint_analyze.py:153-160) over spreadpeaks (:162-197):
+ *   out[i] = max(base[i] (0 when base is NULL), max over the local maxima p of `vector`
+ *                (locmax, :36-52) of vector[p] * table[i + n - p]),  0 <= i < n
+ * `table` holds the 2n+1 Gaussian values exp(-0.5*((j-n)/width)^2), j = 0..2n, computed by the
+ * host with the reference's NumPy expression (:187-192) so that they are the very doubles it
+ * multiplies by; NULL = computed here with libm for `width`.  All pointers are HOST pointers
+ * (a <=256-element call in the reference); the arithmetic runs on the device. */
+int afp_spread_peaks(afp_ctx* ctx, const double* vector, int32_t n, const double* table, double width,
+                     const double* base, double* out);
+
 /* Exposed for the STFT parity check (north_star: magnitudes within 1e-5):
  * |STFT| of one signal, float64 [T][257] (frame-major), T = 1 + n/256.
  * Replaces np.abs(stft.stft(d, 512, 256, window)) (audfprint_analyze.py:280). */

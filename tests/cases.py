@@ -72,3 +72,12 @@ TABLE_OPS_SEED = 2718
 TABLE_OPS_HASHBITS = 10
 TABLE_OPS_DEPTH = 6
 TABLE_OPS_ROWS = 600
+
+# configs[3] / configs[2] geometry (oracle/make_golden_long.py): 180 s tracks, a table whose
+# 12 time bits alias for them (95 s), 10 s and 200 s queries (the latter > 21k hashes at 4 shifts)
+LONG_SECONDS = 180.0
+LONG_SEEDS = [300, 301, 302]
+LONG_HASHBITS = 16
+LONG_DEPTH = 20
+LONG_MAXTIMEBITS = 12
+LONG_QUERIES = [(0, 10.0), (1, 10.0), (2, 10.0), (1, 170.0)]      # (track index, seconds)
