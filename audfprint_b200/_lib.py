@@ -33,7 +33,7 @@ class AnalyzerParams(C.Structure):
 class MatcherParams(C.Structure):
     _fields_ = [("window", C.c_int32), ("threshcount", C.c_int32), ("search_depth", C.c_int32),
                 ("max_alignments_per_id", C.c_int32), ("publish_candidates", C.c_int32),
-                ("row_capacity", C.c_int32)]
+                ("row_capacity", C.c_int32), ("force_general", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -63,6 +63,8 @@ _SIGS = {
     "afp_fetch_hits": (C.c_int, [_P, _P, C.c_int]),
     "afp_match_batch": (C.c_int, [_P, _P, C.c_int, C.c_int32, _I64P, C.POINTER(MatcherParams), _I64P]),
     "afp_fetch_match_rows": (C.c_int, [_P, _P, C.c_int, _I64P]),
+    "afp_match_general_count": (C.c_int, [_P, _I64P]),
+    "afp_fetch_match_status": (C.c_int, [_P, _P]),
     "afp_fetch_match_candidates": (C.c_int, [_P, _P, _P, C.c_int]),
 }
 

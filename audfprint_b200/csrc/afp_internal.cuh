@@ -56,6 +56,7 @@ struct TableDev {
   DevBuf table, counts, hashesperid;
   int32_t hashbits = 0, depth = 0, maxtimebits = 0;
   int64_t nids = 0;
+  uint32_t hmin = 0;   // smallest hashesperid (fast-path pruning bound); 0 = unknown
   bool loaded = false;
 };
 
@@ -123,6 +124,10 @@ struct afp_ctx {
   TableDev tab;
   DevBuf d_q, d_qoff, d_hit_off, d_hits;
   int64_t nhits = -1, hits_nq = 0;
+  DevBuf d_mfast, d_mqlist;    // fast path: member-hit lists; [count + pad][query list] handed to the general kernel
+  int64_t match_general = 0;   // queries of the last batch the general kernel processed
+  int match_general_h = 0;
+  bool match_fast_ran = false;
   DevBuf d_mscratch, d_mrows, d_mrow_cnt, d_mrow_off, d_mrows_packed, d_mcand, d_mcand_cnt;
   int32_t match_sdepth = 0;
   bool match_published = false;
@@ -162,3 +167,5 @@ int afp_compact_peaks(afp_ctx* c, int shift);
 int afp_spread_peaks_impl(afp_ctx* c, const double* vector, int32_t n, const double* table, double width,
                           const double* base, double* out);
 int afp_launch_scan_i32_to_i64(afp_ctx* c, const int32_t* in, int64_t* out, int64_t n);
+cudaError_t afp_launch_match_fast(const void* match_args, int nctas, cudaStream_t stream);   // afp_match_fast.cu
+extern "C" int afp_table_stats(afp_ctx* c);

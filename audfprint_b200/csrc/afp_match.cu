@@ -16,184 +16,9 @@
 // counts is implementation-defined there; here it is (weight desc, id desc).
 #include <math.h>
 #include <algorithm>
-#include "afp_internal.cuh"
+#include "afp_match_common.cuh"
 
 namespace {
-
-constexpr int MT = 1024;          // threads per matching CTA (one CTA per SM, persistent over the queries)
-constexpr int NW = MT / 32;
-constexpr int KCAP = 1024;        // candidate depth handled by the fast path (search_depth <= KCAP)
-constexpr int GCAP = 1024;        // radix select stops once the undecided set is this small
-constexpr int QCAP = 16384;       // query rows sorted in shared memory to merge probes of one bucket (128 KB)
-constexpr int CSEG = 32768;       // track ids counted per pass in shared memory (u32 counters, the same 128 KB)
-constexpr int64_t HITS_MAX = (int64_t)1 << 30;   // per-query hit capacity (rows * depth): int indexing
-constexpr int HSET_BITS = 11;     // candidate hash set: 2048 entries for <= KCAP = 1024 keys
-constexpr int HSET = 1 << HSET_BITS;
-
-struct MatchArgs {
-  const int32_t* q;        // [sum nq][2]
-  const int64_t* qoff;     // [nq+1] (device)
-  int nqueries;
-  const uint32_t* table;
-  const int32_t* counts;
-  const uint32_t* hpi;
-  int hashbits, depth, mtb;
-  int64_t nids;
-  int window, thresh, sdepth, maxalign;
-  // per-CTA scratch (stride in elements)
-  uint2* hits;      int64_t hits_cap;     // (id, dt + bias)
-  uint32_t* dlist;                        // distinct ids, hits_cap
-  double* wtd;                            // weighted count per dlist entry, hits_cap
-  uint32_t* dts;                          // dt + bias of the candidates' hits, grouped per candidate, hits_cap
-  uint32_t* recs;                         // (id << 8 | weight) of every distinct (bucket, slot), hits_cap
-  uint32_t* rawl;                         // raw count per dlist entry, hits_cap
-  int32_t* hist;    int hist_len;         // dtime histogram
-  int32_t* filt;                          // local-max filtered copy
-  int bias;
-  int32_t* rows;    int row_cap;          // [nqueries][row_cap][7]
-  int32_t* row_cnt;                       // [nqueries] rows produced (may exceed row_cap)
-  // sharded-table mode: publish every query's local top-sdepth candidate list
-  int publish;                            // 0/1
-  double* cand;                           // [nqueries][sdepth][3] = (id, raw, weight)
-  int32_t* cand_cnt;                      // [nqueries][2] = (entries, n_above)
-};
-
-// candidate order: (weighted count desc, id desc); keys are (bits of the positive double, id)
-__device__ __forceinline__ bool key_gt(unsigned long long w1, unsigned i1, unsigned long long w2, unsigned i2) {
-  return w1 > w2 || (w1 == w2 && i1 > i2);
-}
-
-struct Shared {
-  unsigned long long a_w[KCAP + GCAP];   // gathered keys, sorted descending: the top-K' candidates
-  unsigned a_id[KCAP + GCAP];
-  unsigned a_raw[KCAP];
-  int loff[KCAP];        // start of candidate j's dt list
-  int cur[KCAP];         // fill cursor of candidate j's dt list
-  unsigned char pass[KCAP];
-  int rhist[256];        // radix-select digit histogram
-  int wsum[NW];
-  int val[NW], idx[NW];
-  unsigned long long kw[NW];
-  unsigned kid[NW];
-  unsigned nhits, ndist, nabove, ngather, nrec;
-  int dmin, dmax, nrows;
-  int sel_digit, sel_need, sel_m;
-  int segoff[514];       // record range of every id segment (nids < 2^24 -> <= 512 segments)
-  int segcur[512];
-};
-
-// 96-bit composite key (weight bits, id), 12 digits of 8 bits from the top
-__device__ __forceinline__ unsigned key_digit(unsigned long long w, unsigned id, int p) {
-  return p < 8 ? (unsigned)(w >> (56 - 8 * p)) & 0xffu : (id >> (24 - 8 * (p - 8))) & 0xffu;
-}
-// compare the top `nfix` digits of (w,id) with those of the prefix: -1 below, 0 equal, +1 above
-__device__ __forceinline__ int prefix_cmp(unsigned long long w, unsigned id, unsigned long long pw, unsigned pid,
-                                          int nfix) {
-  if (nfix == 0) return 0;
-  if (nfix <= 8) {
-    const int sh = 64 - 8 * nfix;
-    const unsigned long long a = w >> sh, b = pw >> sh;
-    return a > b ? 1 : (a < b ? -1 : 0);
-  }
-  if (w != pw) return w > pw ? 1 : -1;
-  const int sh = 32 - 8 * (nfix - 8);
-  const unsigned a = sh ? id >> sh : id, b = sh ? pid >> sh : pid;
-  return a > b ? 1 : (a < b ? -1 : 0);
-}
-
-// inclusive scan of one int per thread over the CTA (MT threads)
-__device__ __forceinline__ int block_scan_incl(int v, int* wsum) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  __syncthreads();
-  if (lane == 31) wsum[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    int w = wsum[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
-    }
-    wsum[lane] = w;
-  }
-  __syncthreads();
-  return v + (warp ? wsum[warp - 1] : 0);
-}
-
-// (value desc, index asc) arg-max over f[lo..hi] == np.argmax (first max)
-__device__ void block_argmax(const int32_t* f, int lo, int hi, Shared& sh, int& best_v, int& best_i) {
-  const int tid = threadIdx.x;
-  int v = -1, ix = 0x7fffffff;
-  for (int i = lo + tid; i <= hi; i += MT) {
-    const int x = f[i];
-    if (x > v) { v = x; ix = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const int ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
-    if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
-  }
-  __syncthreads();
-  if ((tid & 31) == 0) { sh.val[tid >> 5] = v; sh.idx[tid >> 5] = ix; }
-  __syncthreads();
-  best_v = sh.val[0];
-  best_i = sh.idx[0];
-  for (int w = 1; w < NW; ++w)
-    if (sh.val[w] > best_v || (sh.val[w] == best_v && sh.idx[w] < best_i)) { best_v = sh.val[w]; best_i = sh.idx[w]; }
-}
-
-// Histogram-mode search of one candidate (audfprint_match.py:284-311) given lo/hi of its
-// (already filled) dense histogram; emits rows, restores hist to zero.
-__device__ void candidate_modes(const MatchArgs& a, Shared& sh, int32_t* hist, int32_t* filt, int lo, int hi,
-                                unsigned id, int raw, int rank, int32_t* qrows) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // keep_local_maxes (:70-75, locmax :51-67); zero-extended ends are equivalent
-  for (int i = lo + tid; i <= hi; i += MT) {
-    const int v = __ldcg(hist + i), l = __ldcg(hist + i - 1), r = __ldcg(hist + i + 1);
-    filt[i] = (v >= l && r < v) ? v : 0;
-  }
-  __syncthreads();
-  int found = 0;
-  while (true) {
-    int bv, bi;
-    block_argmax(filt, lo, hi, sh, bv, bi);   // :290 np.argmax = first max
-    if (bv <= a.thresh) break;                // :291
-    // :295 count over +-window (hist is zero outside the touched range)
-    int part = 0;
-    for (int t2 = tid; t2 <= 2 * a.window; t2 += MT) part += __ldcg(hist + bi - a.window + t2);
-    part = __reduce_add_sync(0xffffffffu, part);
-    __syncthreads();
-    if (lane == 0) sh.val[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-      int count = 0;
-      for (int w = 0; w < NW; ++w) count += sh.val[w];
-      const int nr = sh.nrows;
-      if (nr < a.row_cap) {
-        int32_t* row = qrows + (size_t)nr * 7;
-        row[0] = (int32_t)id; row[1] = count; row[2] = bi - a.bias; row[3] = raw;
-        row[4] = rank; row[5] = 0; row[6] = 0;                      // :300-301
-      }
-      sh.nrows = nr + 1;
-    }
-    for (int t2 = tid; t2 <= 2 * a.window; t2 += MT) {              // :307-308
-      const int i = bi - a.window + t2;
-      if (i >= lo && i <= hi) filt[i] = 0;
-    }
-    __syncthreads();
-    ++found;
-    if (found > a.maxalign) break;                                   // :309-311
-  }
-  __syncthreads();
-  for (int i = lo + tid; i <= hi; i += MT) hist[i] = 0;              // restore the scratch
-  __syncthreads();
-}
 
 // raw count of a selected id from its weight: w = raw / hpi correctly rounded, so
 // rint(w * hpi) == raw exactly (raw < 2^21).  hashesperid == 0 (w = inf) falls back to a scan.
@@ -223,10 +48,13 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
   for (int i = tid; i < CSEG / 4; i += MT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
-  for (int qi = blockIdx.x; qi < a.nqueries; qi += gridDim.x) {
+  // every query, or the ones the fast kernel handed over (afp_match_fast.cu)
+  const int nwork = a.qlist ? *a.nlist : a.nqueries;
+  for (int wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    const int qi = a.qlist ? a.qlist[wk] : wk;
     const int64_t q0 = a.qoff[qi];
     const int nq = (int)(a.qoff[qi + 1] - q0);
-    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.nrows = 0; sh.nrec = 0; }
+    if (tid == 0) { sh.nhits = 0; sh.ndist = 0; sh.nabove = 0; sh.ms.nrows = 0; sh.nrec = 0; }
     __syncthreads();
     // ---- probe (hash_table.py:162-173).  A query made of several sub-frame shifts probes
     // the same bucket up to `shifts` times (same hash at neighbouring times): the rows are
@@ -581,7 +409,7 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         dmax = __reduce_max_sync(0xffffffffu, dmax);
         if (lane == 0 && dmax >= 0) { atomicMin(&sh.dmin, dmin); atomicMax(&sh.dmax, dmax); }
         __syncthreads();
-        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, sh.a_id[j], n, j, qrows);
+        candidate_modes(a, sh.ms, hist, filt, sh.dmin, sh.dmax, sh.a_id[j], n, j, qrows);
       }
     } else if (maxdepth > 0) {
       // ---- slow path (search_depth > KCAP): one pass over the distinct
@@ -607,11 +435,11 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
           if (ov && (!bvld || key_gt(ow, oid, bw, bid))) { bw = ow; bid = oid; bvld = true; }
         }
         __syncthreads();
-        if (lane == 0) { sh.kw[warp] = bw; sh.kid[warp] = bid; sh.val[warp] = bvld; }
+        if (lane == 0) { sh.kw[warp] = bw; sh.kid[warp] = bid; sh.ms.val[warp] = bvld; }
         __syncthreads();
         bvld = false;
         for (int w = 0; w < NW; ++w)
-          if (sh.val[w] && (!bvld || key_gt(sh.kw[w], sh.kid[w], bw, bid))) { bw = sh.kw[w]; bid = sh.kid[w]; bvld = true; }
+          if (sh.ms.val[w] && (!bvld || key_gt(sh.kw[w], sh.kid[w], bw, bid))) { bw = sh.kw[w]; bid = sh.kid[w]; bvld = true; }
         if (!bvld) break;
         pw = bw; pid = bid; have_prev = true;
         const int raw = (int)raw_of(a, bw, bid, dlist, rawl, ndist);
@@ -635,12 +463,12 @@ __global__ void __launch_bounds__(MT) afp_match_kernel(MatchArgs a) {
         dmax = __reduce_max_sync(0xffffffffu, dmax);
         if (lane == 0 && dmax >= 0) { atomicMin(&sh.dmin, dmin); atomicMax(&sh.dmax, dmax); }
         __syncthreads();
-        candidate_modes(a, sh, hist, filt, sh.dmin, sh.dmax, bid, raw, rank, qrows);
+        candidate_modes(a, sh.ms, hist, filt, sh.dmin, sh.dmax, bid, raw, rank, qrows);
       }
     }
     __syncthreads();
     if (tid == 0) {
-      a.row_cnt[qi] = sh.nrows;
+      a.row_cnt[qi] = sh.ms.nrows;
       if (a.publish) {
         a.cand_cnt[2 * qi] = maxdepth;
         a.cand_cnt[2 * qi + 1] = nabove;
@@ -693,6 +521,32 @@ __global__ void afp_restrict_ids_kernel(uint32_t* table, int32_t* counts, int64_
   }
   for (int s = k; s < n; ++s) row[s] = 0;
   counts[b] = k;
+}
+
+// smallest non-zero hashesperid and the number of zero entries (tracks removed, or never filled)
+__global__ void afp_hpi_stats_kernel(const uint32_t* hpi, int64_t nids, unsigned* out /* [min, nzero] */) {
+  unsigned mn = 0xffffffffu, nz = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nids; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned h = hpi[i];
+    if (h) mn = min(mn, h); else ++nz;
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], mn); if (nz) atomicAdd(&out[1], nz); }
+}
+// does any live table entry name a track whose hashesperid is zero?  (Then a weight can be
+// infinite and the fast path's pruning bound does not hold: it runs without pruning.)
+__global__ void afp_refzero_kernel(const uint32_t* table, const int32_t* counts, int64_t nbuckets, int depth, int mtb,
+                                   const uint32_t* hpi, int64_t nids, unsigned* flag) {
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= nbuckets) return;
+  const int n = min(depth, counts[b]);
+  bool bad = false;
+  for (int s = threadIdx.x & 31; s < n; s += 32) {
+    const uint32_t id = (table[(size_t)b * depth + s] >> mtb) - 1u;
+    if (id < (uint32_t)nids && hpi[id] == 0u) bad = true;
+  }
+  if (bad) atomicExch(flag, 1u);
 }
 
 __global__ void afp_qmax_kernel(const int32_t* q, int64_t nq, int* out_max, int* out_min) {
@@ -749,6 +603,34 @@ int afp_table_upload(afp_ctx* c, const uint32_t* table, const int32_t* counts, i
   c->tab.maxtimebits = maxtimebits;
   c->tab.nids = nids;
   c->tab.loaded = true;
+  return afp_table_stats(c);
+}
+
+// min(hashesperid) for the fast matching path's pruning bound (0 = do not prune)
+int afp_table_stats(afp_ctx* c) {
+  c->tab.hmin = 0;
+  if (c->tab.nids <= 0) return AFP_OK;
+  AFP_CUDA(c, c->d_tmp.reserve(64));
+  unsigned* d = c->d_tmp.as<unsigned>();
+  const unsigned init[3] = {0xffffffffu, 0u, 0u};
+  AFP_CUDA(c, cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  afp_hpi_stats_kernel<<<296, 256, 0, c->stream>>>(c->tab.hashesperid.as<uint32_t>(), c->tab.nids, d);
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches++;
+  unsigned h[3];
+  AFP_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h[1] != 0u) {          // zero entries exist: harmless as long as no table entry names them
+    const int64_t nb = (int64_t)1 << c->tab.hashbits;
+    afp_refzero_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, c->stream>>>(
+        c->tab.table.as<uint32_t>(), c->tab.counts.as<int32_t>(), nb, c->tab.depth, c->tab.maxtimebits,
+        c->tab.hashesperid.as<uint32_t>(), c->tab.nids, d + 2);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    AFP_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->tab.hmin = (h[0] != 0xffffffffu && h[2] == 0u) ? h[0] : 0u;
   return AFP_OK;
 }
 
@@ -944,11 +826,38 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
     c->match_published = true;
   }
   c->match_row_cap = a.row_cap;
+  // ---- fast path first (afp_match_fast.cu); whatever it cannot take goes to the general kernel
+  a.qlist = nullptr;
+  a.nlist = nullptr;
+  a.fstat = nullptr;
+  c->match_fast_ran = false;
+  a.mhits = nullptr;
+  a.mh_cap = 0;
+  a.hmin = c->tab.hmin;
+  a.bm_exact = c->tab.nids <= ((int64_t)1 << 20) ? 1 : 0;
+  const bool fast = !p->force_general && p->threshcount >= 1 && p->search_depth >= 1 && c->tab.depth <= 65535 &&
+                    a.hist_len < (1 << 30);
+  c->match_general = nqueries;
+  if (fast) {
+    a.mh_cap = (int)std::min<int64_t>(a.hits_cap, 65536);
+    AFP_CUDA(c, c->d_mfast.reserve(sizeof(uint2) * (size_t)a.mh_cap * (size_t)nctas));
+    AFP_CUDA(c, c->d_mqlist.reserve(sizeof(int32_t) * (size_t)(9 * nqueries + 4)));
+    a.mhits = c->d_mfast.as<uint2>();
+    a.nlist = c->d_mqlist.as<int>();
+    a.qlist = c->d_mqlist.as<int32_t>() + 4;
+    a.fstat = a.qlist + nqueries;
+    AFP_CUDA(c, cudaMemsetAsync(a.nlist, 0, sizeof(int), c->stream));
+    AFP_CUDA(c, afp_launch_match_fast(&a, nctas, c->stream));
+    c->launches++;
+    c->match_fast_ran = true;
+  }
   AFP_CUDA(c, cudaFuncSetAttribute(afp_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(QCAP * sizeof(unsigned long long))));
   afp_match_kernel<<<nctas, MT, QCAP * sizeof(unsigned long long), c->stream>>>(a);
   AFP_CUDA(c, cudaGetLastError());
   c->launches++;
+  if (fast)
+    AFP_CUDA(c, cudaMemcpyAsync(&c->match_general_h, a.nlist, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   // clamp counts to the capacity (flagging overflow), scan, pack
   int* d_over = c->d_mrow_cnt.as<int>() + nqueries + 1;
   AFP_CUDA(c, cudaMemsetAsync(d_over, 0, sizeof(int), c->stream));
@@ -964,6 +873,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
                               cudaMemcpyDeviceToHost, c->stream));
   AFP_CUDA(c, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (fast) c->match_general = c->match_general_h;     // (the stream was synchronised above)
   if (over) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "row capacity exceeded: a query produced more rows than afp_matcher_params.row_capacity");
   AFP_CUDA(c, c->d_mrows_packed.reserve(sizeof(int32_t) * 7 * (size_t)(total + 1)));
   if (total > 0) {
@@ -974,6 +884,28 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   }
   c->match_total_rows = total;
   if (total_rows) *total_rows = total;
+  return AFP_OK;
+}
+
+int afp_match_general_count(afp_ctx* c, int64_t* n) {
+  if (!c || !n) return AFP_ERR_INVALID;
+  if (c->match_total_rows < 0) AFP_FAIL(c, AFP_ERR_STATE, "afp_match_batch has not been called");
+  *n = c->match_general;
+  return AFP_OK;
+}
+
+int afp_fetch_match_status(afp_ctx* c, int32_t* status) {
+  if (!c || !status) return AFP_ERR_INVALID;
+  if (c->match_total_rows < 0) AFP_FAIL(c, AFP_ERR_STATE, "afp_match_batch has not been called");
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  if (!c->match_fast_ran) {
+    for (int i = 0; i < 8 * c->match_nq; ++i) status[i] = -1;
+    return AFP_OK;
+  }
+  if (c->match_nq > 0)
+    AFP_CUDA(c, cudaMemcpyAsync(status, c->d_mqlist.as<int32_t>() + 4 + c->match_nq, sizeof(int32_t) * 8 * (size_t)c->match_nq,
+                                cudaMemcpyDeviceToHost, c->stream));
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
   return AFP_OK;
 }
 

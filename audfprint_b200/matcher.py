@@ -40,7 +40,8 @@ class Matcher(object):
         if self.illustrate:
             raise NotImplementedError("illustrate is not implemented (SURVEY.md §8f-4)")
         return _lib.MatcherParams(int(self.window), int(self.threshcount), int(self.search_depth),
-                                  int(self.max_alignments_per_id), 0, 0)
+                                  int(self.max_alignments_per_id), 0, 0,
+                                  1 if getattr(self, "force_general_kernel", False) else 0)
 
     @staticmethod
     def _run(ctx, p, packed, nq, qoff):
@@ -60,6 +61,23 @@ class Matcher(object):
                 if cap >= bound:
                     raise
                 cap = min(cap * 8, bound)
+
+    @staticmethod
+    def last_general_count(ht):
+        """Queries of the last device call that the general kernel (not the fast one) processed."""
+        ctx = _lib.context(ht.device)
+        n = C.c_int64(0)
+        ctx.check(ctx.lib.afp_match_general_count(ctx.h, C.byref(n)))
+        return int(n.value)
+
+    @staticmethod
+    def last_status(ht, nqueries):
+        """int32 (nqueries, 8) of the last device call (afp_fetch_match_status): column 0 is 0 for the
+        fast kernel, > 0 = reason for the general kernel, -1 = the fast kernel did not run."""
+        ctx = _lib.context(ht.device)
+        st = np.zeros((max(nqueries, 1), 8), np.int32)
+        ctx.check(ctx.lib.afp_fetch_match_status(ctx.h, st.ctypes.data))
+        return st[:nqueries]
 
     def match_batch(self, ht, queries, sort=True):
         """Match many queries in one device call.

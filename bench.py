@@ -271,6 +271,25 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
     e1.record(stream)
     torch.cuda.synchronize()
     dev_s = e0.elapsed_time(e1) * 1e-3 / steps
+    st = Matcher.last_status(ht, nq)
+    fast_stats = {"queries_on_fast_kernel": int(np.sum(st[:, 0] == 0)),
+                  "queries_handed_to_general_kernel": int(np.sum(st[:, 0] > 0)),
+                  "handover_reasons": {str(k): int(v) for k, v in zip(*np.unique(st[st[:, 0] > 0, 0], return_counts=True))},
+                  "mean_multi_record_ids": float(st[:, 1].mean()), "mean_member_hits": float(st[:, 2].mean()),
+                  "mean_single_record_ids_admitted": float(st[:, 3].mean()),
+                  "mean_ids_above_threshcount": float(st[:, 5].mean())}
+    # A/B: the general kernel alone on the same batch
+    pg = m._params()
+    pg.force_general = 1
+    ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(pg), C.byref(tot)))
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(2):
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(pg), C.byref(tot)))
+    g1.record(stream)
+    torch.cuda.synchronize()
+    gen_s = g0.elapsed_time(g1) * 1e-3 / 2
     # --- audio -> result (fingerprint 4 shifts + match), host PCM in
     t0 = time.perf_counter()
     r2, o2 = qan.fingerprint_packed(hqn, qoffs, sample_lengths=qlens)
@@ -292,7 +311,9 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
            "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": nprobe,
                         "achieved": nprobe / dev_s / 1e9, "unit": "GB/s", "peak": measured_peaks()[0],
                         "frac": nprobe / dev_s / 1e9 / measured_peaks()[0]},
-           "top1_correct": correct, "cpu_baseline": None, "parity": None}
+           "top1_correct": correct, "fast_kernel": fast_stats,
+           "general_kernel_only": {"value": nq / gen_s, "unit": "queries/s", "ms_per_step": gen_s * 1e3},
+           "cpu_baseline": None, "parity": None}
     if want_cpu:
         ns = min(a.match_cpu_sample, nq)
         _TABLE = (table, counts, hashbits, depth, mtb, hpi)

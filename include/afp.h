@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AFP_ABI_VERSION 1
+#define AFP_ABI_VERSION 2
 
 typedef struct afp_ctx afp_ctx;
 
@@ -83,6 +83,9 @@ typedef struct {
                                   * to search_depth * (max_alignments_per_id + 1); a query that
                                   * produces more than this returns AFP_ERR_UNSUPPORTED and the
                                   * caller retries with a larger capacity                       */
+  int32_t force_general;         /* 0 = the fast kernel takes every query inside its capacities and
+                                  * hands the rest to the general kernel (identical results);
+                                  * 1 = general kernel only (tests, A/B timing)                  */
 } afp_matcher_params;
 
 /* ---- context --------------------------------------------------------------- */
@@ -199,6 +202,18 @@ int afp_match_batch(afp_ctx* ctx, const int32_t* q_rows, int q_on_host, int32_t 
                     const int64_t* q_offsets, const afp_matcher_params* p,
                     int64_t* total_rows);
 int afp_fetch_match_rows(afp_ctx* ctx, int32_t* rows, int rows_on_host, int64_t* row_offsets);
+/* How many queries of the last afp_match_batch went through the general kernel (all of them
+ * with force_general; otherwise the ones outside the fast kernel's capacities). */
+int afp_match_general_count(afp_ctx* ctx, int64_t* n);
+/* Per query of the last batch, HOST int32 [nqueries][8]:
+ *   [0] 0 = the fast kernel finished it, > 0 = why it was handed to the general kernel
+ *       (1 multi-record id set full, 2 member-hit list full, 3 too many single-record ids outrank
+ *       the K-th member, 4 shard mode with > 2^20 ids and fewer members than search_depth,
+ *       5 candidate depth > 1024), -1 = the fast kernel did not run;
+ *   [1] multi-record ids, [2] their hits, [3] single-record ids admitted by pass 3,
+ *   [4] candidate depth, [5] ids above threshcount, [6] largest bucket multiplicity, [7] distinct
+ *       ids (shard mode only). */
+int afp_fetch_match_status(afp_ctx* ctx, int32_t* status);
 /* After afp_match_batch with publish_candidates = 1: `cand` float64
  * [nqueries][search_depth][3] = (id, raw count, weighted count) in (weight desc, id desc)
  * order, `counts` int32 [nqueries][2] = (entries used, #ids with raw > threshcount). */
