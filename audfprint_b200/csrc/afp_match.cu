@@ -839,7 +839,7 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
                     a.hist_len < (1 << 30);
   c->match_general = nqueries;
   if (fast) {
-    a.mh_cap = (int)std::min<int64_t>(a.hits_cap, 65536);
+    a.mh_cap = (int)std::min<int64_t>(std::max<int64_t>((a.hits_cap + 31) / 32 * 32, 32768), 131072);   // 32 per-warp segments
     AFP_CUDA(c, c->d_mfast.reserve(sizeof(uint2) * (size_t)a.mh_cap * (size_t)nctas));
     AFP_CUDA(c, c->d_mqlist.reserve(sizeof(int32_t) * (size_t)(9 * nqueries + 4)));
     a.mhits = c->d_mfast.as<uint2>();

@@ -43,6 +43,7 @@ constexpr int MMAX = 12288;                 // members the set may hold (load fa
 constexpr int QF = 2048;                    // query rows sorted per chunk
 constexpr int SCAP = 4096;                  // rank-sort capacity: selected members + admitted single-record ids
 constexpr int XCAP = 1024;                  // single-record ids pass 3 may admit
+constexpr int PROBE_MAX = 256;              // insertion gives up (set full) after this many probes
 constexpr int WBINS = 4096;                 // weight histogram bins (float image of the weight, top 16 bits)
 // why a query was handed to the general kernel (afp_fetch_match_status)
 enum { FS_DONE = 0, FS_SET_FULL = 1, FS_HITS_FULL = 2, FS_EXTRAS_FULL = 3, FS_NDIST_UNKNOWN = 4, FS_DEPTH = 5,
@@ -60,11 +61,14 @@ constexpr int OFF_SRAW = OFF_SID + SCAP * 4;               //   u32 sraw[SCAP]
 constexpr int OFF_MKEYS = OFF_R0 + BM_WORDS * 4;           // u32 mkeys[MSLOTS] (id + 1, 0 = empty)
 constexpr int OFF_Q = OFF_MKEYS + MSLOTS * 4;              // u64 qkeys[QF]
 constexpr int OFF_HPOS = OFF_Q + QF * 8;                   // u16 hpos[QF], hm[QF], hn[QF]
+constexpr int GBINS = 1024;                                //   int gbin[GBINS]: counting sort of the chunk
+constexpr int OFF_GBIN = OFF_HPOS + QF * 6;
 constexpr int OFF_MAP = OFF_Q;                             //   u16 map16[MSLOTS]           (routing)
 constexpr int FAST_SMEM = OFF_HPOS + QF * 8;               // 229376 B
 static_assert(OFF_SRAW + SCAP * 4 == OFF_MKEYS, "rank arrays fill the upper half of R0");
 static_assert(WBINS * 4 <= SCAP * 8, "weight histogram fits under sw");
 static_assert(MSLOTS * 2 <= QF * 16, "slot map fits R2");
+static_assert(OFF_GBIN + GBINS * 4 <= OFF_HPOS + QF * 8, "bin counters fit behind the group arrays");
 // after the final sort only the first KCAP ranks are alive: the dt-list bookkeeping of the
 // candidates reuses the tail of sid[]
 constexpr int OFF_LOFF = OFF_SID + KCAP * 4;
@@ -75,6 +79,7 @@ static_assert(OFF_PASS + KCAP <= OFF_SRAW, "candidate bookkeeping fits behind si
 struct FastShared {
   ModeScratch ms;
   int wsum[NW];
+  int wcount[NW];          // hits in every warp's segment of the member-hit list
   unsigned nmem, nmh, nx, nabove, ndist, mmax, ngath;
   int overflow;
   int dmin, dmax;
@@ -114,24 +119,47 @@ __device__ int prepare_chunk(const MatchArgs& a, FastShared& fs, unsigned char* 
   unsigned short* hn = hm + QF;
   const int tid = threadIdx.x;
   const uint32_t hmask = (1u << a.hashbits) - 1u;
-  int n2 = 2;
-  while (n2 < n) n2 <<= 1;
-  for (int i = tid; i < n2; i += MT)
-    qkeys[i] = i < n ? ((unsigned long long)((uint32_t)a.q[2 * (row0 + i) + 1] & hmask) << 32) |
-                           (uint32_t)a.q[2 * (row0 + i)]
-                     : ~0ull;
+  // Group the rows by bucket without a full sort: counting sort into GBINS hash bins of the
+  // bucket (two shared-memory atomics per row), then every bin's handful of keys is put in
+  // order by one thread.  Equal buckets end up adjacent, their times ascending.
+  int* gbin = reinterpret_cast<int*>(smem + OFF_GBIN);
+  static_assert(GBINS == MT, "one thread per bin");
+  gbin[tid] = 0;
   __syncthreads();
-  for (int k = 2; k <= n2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n2; i += MT) {
-        const int l = i ^ j;
-        if (l > i) {
-          const unsigned long long x = qkeys[i], y = qkeys[l];
-          if ((x > y) == ((i & k) == 0)) { qkeys[i] = y; qkeys[l] = x; }
-        }
-      }
-      __syncthreads();
+  unsigned long long key[QF / MT];
+  int bin[QF / MT];
+#pragma unroll
+  for (int u = 0; u < QF / MT; ++u) {
+    const int i = tid + u * MT;
+    bin[u] = -1;
+    if (i < n) {
+      const uint32_t b = (uint32_t)a.q[2 * (row0 + i) + 1] & hmask;
+      key[u] = ((unsigned long long)b << 32) | (uint32_t)a.q[2 * (row0 + i)];
+      bin[u] = (int)((b * 0x9E3779B1u) >> 22);
+      atomicAdd(&gbin[bin[u]], 1);
     }
+  }
+  __syncthreads();
+  {
+    const int c = gbin[tid];
+    const int incl = block_scan_incl(c, fs.wsum);       // (barriers inside)
+    gbin[tid] = incl - c;                               // start of the bin
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < QF / MT; ++u)
+    if (bin[u] >= 0) qkeys[atomicAdd(&gbin[bin[u]], 1)] = key[u];
+  __syncthreads();                                      // gbin[t] is now the END of bin t
+  {
+    const int lo = tid ? gbin[tid - 1] : 0, hi = gbin[tid];
+    for (int i = lo + 1; i < hi; ++i) {                 // insertion sort of a few keys
+      const unsigned long long x = qkeys[i];
+      int j = i;
+      while (j > lo && qkeys[j - 1] > x) { qkeys[j] = qkeys[j - 1]; --j; }
+      qkeys[j] = x;
+    }
+  }
+  __syncthreads();
   int base = 0;
   for (int i0 = 0; i0 < n; i0 += MT) {
     const int i = i0 + tid;
@@ -177,6 +205,8 @@ __device__ void scan_chunk(const MatchArgs& a, FastShared& fs, unsigned char* sm
   const uint32_t tmask = (1u << a.mtb) - 1u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const double wk_d = __longlong_as_double((long long)wk);
+  const int wcap = a.mh_cap / NW;                     // pass 2: hits this warp may append
+  int wcount = PASS == 2 ? fs.wcount[warp] : 0;
 
   uint32_t nv[4] = {0u, 0u, 0u, 0u};
   auto fetch = [&](int g, uint32_t (&v)[4]) {          // first 128 slots of group g
@@ -217,16 +247,16 @@ __device__ void scan_chunk(const MatchArgs& a, FastShared& fs, unsigned char* sm
             const unsigned h = bm_index(id, a.bm_exact);
             const unsigned bit = 1u << (h & 31u);
             const unsigned old = atomicOr(&bm[h >> 5], bit);
-            if (((old & bit) || m > a.thresh) && !*(volatile int*)&fs.overflow) {
+            if ((old & bit) || m > a.thresh) {
+              // join the member set; a probe sequence of PROBE_MAX means the set is (nearly) full:
+              // the query is handed over (the members are counted after the pass)
               const unsigned key = id + 1u;
               unsigned s = set_hash(id);
+              int tries = 0;
               while (true) {
                 const unsigned k = atomicCAS(&mkeys[s], 0u, key);
-                if (k == 0u) {
-                  if (atomicAdd(&fs.nmem, 1u) >= (unsigned)MMAX) fs.overflow = FS_SET_FULL;
-                  break;
-                }
-                if (k == key) break;
+                if (k == 0u || k == key) break;
+                if (++tries >= PROBE_MAX) { fs.overflow = FS_SET_FULL; break; }
                 s = (s + 1u) & (MSLOTS - 1);
               }
             }
@@ -240,19 +270,17 @@ __device__ void scan_chunk(const MatchArgs& a, FastShared& fs, unsigned char* sm
           // every member entry appends its m hits; m is the same for the whole group, so the
           // positions come from one ballot and one atomic per warp
           const unsigned mem = __ballot_sync(0xffffffffu, slot >= 0);
-          if (mem) {
+          if (mem) {                                    // this warp's own segment of the list: no atomics
             const int total = __popc(mem) * m;
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&fs.nmh, (unsigned)total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned)total > (unsigned)a.mh_cap) {
+            if (wcount + total > wcap) {
               fs.overflow = FS_HITS_FULL;
             } else if (slot >= 0) {
               const int rt = (int)(v[u] & tmask) + a.bias;
-              uint2* dst = mhits + base + __popc(mem & lt_mask) * m;
+              uint2* dst = mhits + (size_t)warp * wcap + wcount + __popc(mem & lt_mask) * m;
               for (int k = 0; k < m; ++k)
                 dst[k] = make_uint2((unsigned)slot, (unsigned)(rt - (int)(uint32_t)qkeys[r + k]));
             }
+            wcount += total;
           }
         } else {
           if (ok && set_find(mkeys, id) < 0) {
@@ -274,6 +302,7 @@ __device__ void scan_chunk(const MatchArgs& a, FastShared& fs, unsigned char* sm
     }
     g = gn;
   }
+  if (PASS == 2 && lane == 0) fs.wcount[warp] = min(wcount, wcap);
 }
 
 // descending bitonic sort of (sw, sid) with sraw carried along; n2 a power of two <= SCAP
@@ -331,6 +360,7 @@ __global__ void __launch_bounds__(MT) afp_match_fast_kernel(MatchArgs a) {
       fs.nmem = 0; fs.nmh = 0; fs.nx = 0; fs.nabove = 0; fs.ndist = 0; fs.mmax = 0; fs.ngath = 0;
       fs.overflow = 0; fs.ms.nrows = 0;
     }
+    if (tid < NW) fs.wcount[tid] = 0;
     zero_r0((BM_WORDS + MSLOTS) * 4);              // the "seen" bitmap and the member keys
     __syncthreads();
     int handover = FS_DONE;
@@ -357,20 +387,32 @@ __global__ void __launch_bounds__(MT) afp_match_fast_kernel(MatchArgs a) {
         // ---- "member" bitmap, then pass 2: the hits of the members ---------------------------
         zero_r0(BM_WORDS * 4);
         __syncthreads();
+        unsigned nm = 0;
         for (int s = tid; s < MSLOTS; s += MT) {
           const unsigned key = mkeys[s];
           if (key) {
             const unsigned h = bm_index(key - 1u, a.bm_exact);
             atomicOr(&bm[h >> 5], 1u << (h & 31u));
+            ++nm;
           }
         }
+        nm = __reduce_add_sync(0xffffffffu, nm);
+        if (lane == 0 && nm) atomicAdd(&fs.nmem, nm);
         __syncthreads();
+        if (fs.nmem > (unsigned)MMAX) handover = FS_SET_FULL;      // (uniform)
+      }
+      if (!handover) {
         for (int c0 = 0; c0 < nq; c0 += QF) {
           const int G = single ? G1 : prepare_chunk(a, fs, smem, q0 + c0, min(QF, nq - c0));
           scan_chunk<2>(a, fs, smem, G, mhits, 0ull, 0u, 0);
           __syncthreads();
         }
         handover = fs.overflow;
+        if (tid == 0) {
+          unsigned t = 0;
+          for (int w = 0; w < NW; ++w) t += (unsigned)fs.wcount[w];
+          fs.nmh = t;
+        }
         __syncthreads();
       }
       int M = 0;                                   // entries in the rank arrays
@@ -378,8 +420,11 @@ __global__ void __launch_bounds__(MT) afp_match_fast_kernel(MatchArgs a) {
         // ---- exact raw counts = histogram of the member-hit list over the set slots ----------
         zero_r0((MSLOTS + WBINS) * 4);             // counters + weight histogram
         __syncthreads();
-        const int nmh = (int)fs.nmh;
-        for (int i = tid; i < nmh; i += MT) atomicAdd(&mcnt[mhits[i].x], 1u);
+        {
+          const int wcap = a.mh_cap / NW, n = fs.wcount[warp];
+          const uint2* seg = mhits + (size_t)warp * wcap;
+          for (int i = lane; i < n; i += 32) atomicAdd(&mcnt[seg[i].x], 1u);
+        }
         __syncthreads();
         // ---- select: histogram of the weights' float image, #ids above threshcount -----------
         unsigned above = 0;
@@ -513,17 +558,20 @@ __global__ void __launch_bounds__(MT) afp_match_fast_kernel(MatchArgs a) {
         if (rowable) map16[set_find(mkeys, id)] = (unsigned short)tid;     // raw > threshcount: a member
         __syncthreads();
         // ---- route the member hits of the row-capable candidates to their dt lists ----------
-        const int nmh = (int)fs.nmh;
-        for (int i0 = 0; i0 < nmh; i0 += 4 * MT) {
-          uint2 h4[4];
+        {
+          const int wcap = a.mh_cap / NW, n = fs.wcount[warp];
+          const uint2* seg = mhits + (size_t)warp * wcap;
+          for (int i0 = 0; i0 < n; i0 += 128) {
+            uint2 h4[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            h4[u] = (i0 + u * MT + tid < nmh) ? mhits[i0 + u * MT + tid] : make_uint2(0xffffffffu, 0u);
+            for (int u = 0; u < 4; ++u)
+              h4[u] = (i0 + 32 * u + lane < n) ? seg[i0 + 32 * u + lane] : make_uint2(0xffffffffu, 0u);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (h4[u].x == 0xffffffffu) continue;
-            const unsigned j = map16[h4[u].x];
-            if (j != 0xffffu) dts[loff[j] + atomicAdd(&cur[j], 1)] = h4[u].y;
+            for (int u = 0; u < 4; ++u) {
+              if (h4[u].x == 0xffffffffu) continue;
+              const unsigned j = map16[h4[u].x];
+              if (j != 0xffffu) dts[loff[j] + atomicAdd(&cur[j], 1)] = h4[u].y;
+            }
           }
         }
         __syncthreads();
