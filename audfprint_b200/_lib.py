@@ -58,6 +58,13 @@ _SIGS = {
     "afp_stft_mag": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, _P, C.c_int]),
     "afp_sgram": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, _P, C.c_int]),
     "afp_table_upload": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, C.c_int]),
+    "afp_table_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "afp_table_set_hashesperid": (C.c_int, [_P, _P, C.c_int64]),
+    "afp_table_store_batch": (C.c_int, [_P, _P, C.c_int, _I64P, C.c_int32, _I64P, _I64P]),
+    "afp_table_fetch_overflow": (C.c_int, [_P, _P, _P, _P]),
+    "afp_table_apply_patches": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "afp_table_download": (C.c_int, [_P, _P, _P]),
+    "afp_mt_randint_replay": (C.c_int, [_P, _P, C.c_int64, _P]),
     "afp_table_restrict_ids": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "afp_get_hits": (C.c_int, [_P, _P, C.c_int64, C.c_int, _I64P]),
     "afp_fetch_hits": (C.c_int, [_P, _P, C.c_int]),
@@ -65,6 +72,9 @@ _SIGS = {
     "afp_fetch_match_rows": (C.c_int, [_P, _P, C.c_int, _I64P]),
     "afp_match_general_count": (C.c_int, [_P, _I64P]),
     "afp_fetch_match_status": (C.c_int, [_P, _P]),
+    "afp_shard_record_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "afp_shard_pack": (C.c_int, [_P, C.c_int32, _P]),
+    "afp_shard_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I64P]),
     "afp_fetch_match_candidates": (C.c_int, [_P, _P, _P, C.c_int]),
 }
 
@@ -132,6 +142,7 @@ class Context:
         self.device = device
         self.analyzer_key = None
         self.table_key = None
+        self.table_owner = None      # weakref to the HashTable whose device copy is newer than its host arrays
 
     def check(self, rc):
         if rc != 0:

@@ -214,34 +214,56 @@ class Analyzer(object):
                     start, acc = i, 0
                 acc += f
             return out + self.fingerprint_batch(signals[start:], shifts)
+        packed, starts, lens = self._pack(signals)
+        rows, roff = self.fingerprint_packed(packed, starts, shifts, sample_lengths=lens)
+        return [rows[roff[i]:roff[i + 1]] for i in range(len(signals))]
+
+    def ingest_batch(self, hashtable, names, signals, on_device=True):
+        """Fingerprint many signals and add them to the table (batched Analyzer.ingest,
+        audfprint_analyze.py:430-457).  Returns the hash counts.
+        With on_device (default) the hashes never leave the GPU: every device call of at most
+        `max_frames_per_call` frames fingerprints its files and HashTable.store_batch inserts
+        them straight from the workspace into the device-resident table (bit-identical to
+        per-track store() calls from the same `random` state).  on_device=False keeps the
+        round-1 path: hashes to the host, one store() per file."""
+        if not on_device:
+            hashes = self.fingerprint_batch(signals, self.shifts)
+            for name, sig, h in zip(names, signals, hashes):
+                hashtable.store(name, h)
+                self._account(len(sig) / self.target_sr)
+            return [len(h) for h in hashes]
+        nsh = max(1, int(self.shifts))
+        counts, start, acc = [], 0, 0
+        frames = [nsh * (1 + len(x) // self.n_hop) for x in signals]
+        for i in range(len(signals) + 1):
+            if i == len(signals) or (acc + frames[i] > self.max_frames_per_call and i > start):
+                if i > start:
+                    packed, starts, lens = self._pack(signals[start:i])
+                    self.fingerprint_packed(packed, starts, nsh, fetch=False, sample_lengths=lens)
+                    counts += hashtable.store_batch(names[start:i])
+                start, acc = i, 0
+            if i < len(signals):
+                acc += frames[i]
+        for sig in signals:
+            self._account(len(sig) / self.target_sr)
+        return counts
+
+    @staticmethod
+    def _pack(signals):
+        """Signals -> one packed PCM buffer, every file on a 16-byte boundary (TMA bulk copies)."""
         arrs = [_as_pcm(s) for s in signals]
         kinds = set(k for _, k in arrs)
         if len(kinds) > 1:
             arrs = [(a.astype(np.float32) * np.float32(1.0 / 32768.0) if k == _lib.PCM_I16 else a, _lib.PCM_F32)
                     for a, k in arrs]
         lens = np.array([len(a) for a, _ in arrs], np.int64)
-        # keep every file 16-byte aligned in the packed buffer (TMA bulk copies)
-        esz = arrs[0][0].dtype.itemsize
-        al = 16 // esz
+        al = 16 // arrs[0][0].dtype.itemsize
         starts = np.zeros(len(arrs) + 1, np.int64)
-        for i, n in enumerate(lens):
-            starts[i + 1] = starts[i] + (n + al - 1) // al * al
+        starts[1:] = np.cumsum((lens + al - 1) // al * al)
         packed = np.zeros(int(starts[-1]) + al, arrs[0][0].dtype)
         for (a, _), s in zip(arrs, starts[:-1]):
             packed[s:s + len(a)] = a
-        rows, roff = self.fingerprint_packed(packed, starts, shifts, sample_lengths=lens)
-        return [rows[roff[i]:roff[i + 1]] for i in range(len(arrs))]
-
-    def ingest_batch(self, hashtable, names, signals):
-        """Fingerprint many signals in one device call and add them to the table
-        (batched Analyzer.ingest, audfprint_analyze.py:430-457).  Returns the hash counts.
-        The inserts stay per file on the host (0.2 ms each, measured) so that overflowing
-        buckets draw from `random` in the reference's order."""
-        hashes = self.fingerprint_batch(signals, self.shifts)
-        for name, sig, h in zip(names, signals, hashes):
-            hashtable.store(name, h)
-            self._account(len(sig) / self.target_sr)
-        return [len(h) for h in hashes]
+        return packed, starts, lens
 
     # ---- reference methods -------------------------------------------------------
     def find_peaks(self, d, sr):

@@ -124,6 +124,10 @@ struct afp_ctx {
   TableDev tab;
   DevBuf d_q, d_qoff, d_hit_off, d_hits;
   int64_t nhits = -1, hits_nq = 0;
+  // device-side HashTable.store (afp_store.cu)
+  DevBuf d_st_off, d_st_ids, d_st_eval, d_st_seq, d_st_ovf, d_st_cnt, d_st_seg, d_st_heavy, d_st_part, d_st_scan;
+  DevBuf d_st_obkt, d_st_opos, d_st_oval;
+  int64_t store_novf = 0;
   DevBuf d_mfast, d_mqlist;    // fast path: member-hit lists; [count + pad][query list] handed to the general kernel
   int64_t match_general = 0;   // queries of the last batch the general kernel processed
   int match_general_h = 0;
@@ -169,3 +173,5 @@ int afp_spread_peaks_impl(afp_ctx* c, const double* vector, int32_t n, const dou
 int afp_launch_scan_i32_to_i64(afp_ctx* c, const int32_t* in, int64_t* out, int64_t n);
 cudaError_t afp_launch_match_fast(const void* match_args, int nctas, cudaStream_t stream);   // afp_match_fast.cu
 extern "C" int afp_table_stats(afp_ctx* c);
+int afp_finish_match_rows(afp_ctx* c, int nqueries, int row_cap, int64_t* total_out);
+int afp_scan_large(afp_ctx* c, const int32_t* in, int64_t* out, int64_t n);   // afp_store.cu

@@ -578,6 +578,39 @@ __global__ void afp_clamp_kernel(const int32_t* in, int n, int cap, int32_t* out
 
 }  // namespace
 
+// Rows of a batch sit at a fixed stride (row_cap per query) in d_mrows with their counts in
+// d_mrow_cnt: clamp the counts to the capacity (flagging overflow), scan, pack -> d_mrows_packed,
+// d_mrow_off (what afp_fetch_match_rows returns).
+int afp_finish_match_rows(afp_ctx* c, int nqueries, int row_cap, int64_t* total_out) {
+  int* d_over = c->d_mrow_cnt.as<int>() + nqueries + 1;
+  AFP_CUDA(c, cudaMemsetAsync(d_over, 0, sizeof(int), c->stream));
+  AFP_CUDA(c, c->d_tmp.reserve(sizeof(int32_t) * (size_t)(nqueries + 8)));
+  afp_clamp_kernel<<<(nqueries + 255) / 256, 256, 0, c->stream>>>(c->d_mrow_cnt.as<int32_t>(), nqueries, row_cap,
+                                                                  c->d_tmp.as<int32_t>(), d_over);
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches++;
+  int rc;
+  if ((rc = afp_launch_scan_i32_to_i64(c, c->d_tmp.as<int32_t>(), c->d_mrow_off.as<int64_t>(), nqueries))) return rc;
+  int64_t total = 0;
+  int over = 0;
+  AFP_CUDA(c, cudaMemcpyAsync(&total, c->d_mrow_off.as<int64_t>() + nqueries, sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, c->stream));
+  AFP_CUDA(c, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (over) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "row capacity exceeded: a query produced more rows than afp_matcher_params.row_capacity");
+  AFP_CUDA(c, c->d_mrows_packed.reserve(sizeof(int32_t) * 7 * (size_t)(total + 1)));
+  if (total > 0) {
+    afp_pack_rows_kernel<<<nqueries, 64, 0, c->stream>>>(c->d_mrows.as<int32_t>(), c->d_mrow_cnt.as<int32_t>(),
+                                                         c->d_mrow_off.as<int64_t>(), row_cap,
+                                                         c->d_mrows_packed.as<int32_t>());
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches++;
+  }
+  c->match_total_rows = total;
+  *total_out = total;
+  return AFP_OK;
+}
+
 extern "C" {
 
 int afp_table_upload(afp_ctx* c, const uint32_t* table, const int32_t* counts, int32_t hashbits, int32_t depth,
@@ -858,31 +891,9 @@ int afp_match_batch(afp_ctx* c, const int32_t* q_rows, int q_on_host, int32_t nq
   c->launches++;
   if (fast)
     AFP_CUDA(c, cudaMemcpyAsync(&c->match_general_h, a.nlist, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  // clamp counts to the capacity (flagging overflow), scan, pack
-  int* d_over = c->d_mrow_cnt.as<int>() + nqueries + 1;
-  AFP_CUDA(c, cudaMemsetAsync(d_over, 0, sizeof(int), c->stream));
-  AFP_CUDA(c, c->d_tmp.reserve(sizeof(int32_t) * (size_t)(nqueries + 8)));
-  afp_clamp_kernel<<<(nqueries + 255) / 256, 256, 0, c->stream>>>(a.row_cnt, nqueries, a.row_cap,
-                                                                  c->d_tmp.as<int32_t>(), d_over);
-  AFP_CUDA(c, cudaGetLastError());
-  c->launches++;
-  if ((rc = afp_launch_scan_i32_to_i64(c, c->d_tmp.as<int32_t>(), c->d_mrow_off.as<int64_t>(), nqueries))) return rc;
   int64_t total = 0;
-  int over = 0;
-  AFP_CUDA(c, cudaMemcpyAsync(&total, c->d_mrow_off.as<int64_t>() + nqueries, sizeof(int64_t),
-                              cudaMemcpyDeviceToHost, c->stream));
-  AFP_CUDA(c, cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (fast) c->match_general = c->match_general_h;     // (the stream was synchronised above)
-  if (over) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "row capacity exceeded: a query produced more rows than afp_matcher_params.row_capacity");
-  AFP_CUDA(c, c->d_mrows_packed.reserve(sizeof(int32_t) * 7 * (size_t)(total + 1)));
-  if (total > 0) {
-    afp_pack_rows_kernel<<<nqueries, 64, 0, c->stream>>>(a.rows, a.row_cnt, c->d_mrow_off.as<int64_t>(), a.row_cap,
-                                                         c->d_mrows_packed.as<int32_t>());
-    AFP_CUDA(c, cudaGetLastError());
-    c->launches++;
-  }
-  c->match_total_rows = total;
+  if ((rc = afp_finish_match_rows(c, nqueries, a.row_cap, &total))) return rc;
+  if (fast) c->match_general = c->match_general_h;     // (the stream was synchronised)
   if (total_rows) *total_rows = total;
   return AFP_OK;
 }

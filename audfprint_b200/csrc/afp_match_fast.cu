@@ -42,7 +42,7 @@ constexpr int MSLOTS = 16384;               // open-addressing set of multi-reco
 constexpr int MMAX = 12288;                 // members the set may hold (load factor <= 0.75)
 constexpr int QF = 2048;                    // query rows sorted per chunk
 constexpr int SCAP = 4096;                  // rank-sort capacity: selected members + admitted single-record ids
-constexpr int XCAP = 1024;                  // single-record ids pass 3 may admit
+constexpr int XCAP = 2048;                  // single-record ids pass 3 may admit
 constexpr int PROBE_MAX = 256;              // insertion gives up (set full) after this many probes
 constexpr int WBINS = 4096;                 // weight histogram bins (float image of the weight, top 16 bits)
 // why a query was handed to the general kernel (afp_fetch_match_status)

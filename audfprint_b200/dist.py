@@ -111,56 +111,70 @@ def merge_sharded_results(shard_records, search_depth: int):
 
 
 # ---- the one exchange step of the sharded-table match --------------------------------
-def pack_shard_records(records, search_depth: int, row_cap: int) -> np.ndarray:
-    """Fixed-size float64 record per query: [n_above, ncand, nrows, cand(sd x 3), rows(row_cap x 7)]
-    (ints < 2^53 are exact in float64)."""
+# Wire format = the byte records of csrc/afp_shard.cu (afp_shard_pack / afp_shard_merge): per
+# query  int32 {n_above, ncand, nrows, 0}; f64 weight[sd]; uint32 id[sd]; uint32 raw[sd];
+# int32 rows[row_cap][7].  The NumPy pack / merge below are the host-side statement of the same
+# format and the same merge: they serve the CPU (gloo) tests and check the device kernels; the
+# product path (match_sharded_batch) packs, gathers and merges on the device.
+def record_dtype(search_depth: int, row_cap: int) -> np.dtype:
     sd = max(int(search_depth), 1)
-    w = 3 + 3 * sd + 7 * row_cap
-    out = np.zeros((len(records), w), np.float64)
+    if row_cap < 2 or row_cap % 2:
+        raise ValueError("row_cap must be even and >= 2")
+    return np.dtype([("hdr", "<i4", (4,)), ("w", "<f8", (sd,)), ("id", "<u4", (sd,)), ("raw", "<u4", (sd,)),
+                     ("rows", "<i4", (row_cap, 7))])
+
+
+def pack_shard_records(records, search_depth: int, row_cap: int) -> np.ndarray:
+    """List of per-query dicts (match_batch_shard) -> structured array (nq,) in the wire format."""
+    out = np.zeros(len(records), record_dtype(search_depth, row_cap))
+    sd = out.dtype["w"].shape[0]
     for i, r in enumerate(records):
         c = np.asarray(r["cand"], np.float64).reshape(-1, 3)[:sd]
-        rows = np.asarray(r["rows"], np.float64).reshape(-1, 7)
+        rows = np.asarray(r["rows"], np.int32).reshape(-1, 7)
         if len(rows) > row_cap:
             raise ValueError("a shard produced %d rows for one query, row_cap is %d" % (len(rows), row_cap))
-        out[i, 0], out[i, 1], out[i, 2] = r["n_above"], len(c), len(rows)
-        out[i, 3:3 + 3 * len(c)] = c.ravel()
-        out[i, 3 + 3 * sd:3 + 3 * sd + 7 * len(rows)] = rows.ravel()
+        out["hdr"][i, :3] = (r["n_above"], len(c), len(rows))
+        out["id"][i, :len(c)], out["raw"][i, :len(c)], out["w"][i, :len(c)] = c[:, 0], c[:, 1], c[:, 2]
+        out["rows"][i, :len(rows)] = rows
     return out
 
 
-def unpack_shard_records(buf: np.ndarray, search_depth: int, row_cap: int):
-    sd = max(int(search_depth), 1)
+def unpack_shard_records(buf: np.ndarray, search_depth: int = None, row_cap: int = None):
     recs = []
-    for row in buf:
-        nc, nr = int(row[1]), int(row[2])
-        recs.append({"n_above": int(row[0]),
-                     "cand": row[3:3 + 3 * nc].reshape(nc, 3).copy(),
-                     "rows": row[3 + 3 * sd:3 + 3 * sd + 7 * nr].reshape(nr, 7).astype(np.int32)})
+    for r in buf:
+        nc, nr = int(r["hdr"][1]), int(r["hdr"][2])
+        cand = np.stack([r["id"][:nc].astype(np.float64), r["raw"][:nc].astype(np.float64), r["w"][:nc]], axis=1)
+        recs.append({"n_above": int(r["hdr"][0]), "cand": cand, "rows": r["rows"][:nr].copy()})
     return recs
+
+
+def _allgather_bytes(mine: np.ndarray, group=None) -> np.ndarray:
+    """all_gather of one structured array per rank -> (world, nq) structured array."""
+    rank, ws = world()
+    if ws == 1:
+        return mine[None]
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(mine).view(np.uint8).reshape(len(mine), -1)).to(dev)
+    out = torch.empty((ws * t.shape[0], t.shape[1]), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().view(mine.dtype).reshape(ws, len(mine))
 
 
 def allgather_shard_records(records, search_depth: int, row_cap: int = 16, group=None):
     """ONE all-gather (NCCL over NVLink when the group is nccl, gloo on CPU) of the packed
     per-query records of every shard.  Returns per_shard[s][q] record dicts."""
-    rank, ws = world()
-    mine = pack_shard_records(records, search_depth, row_cap)
-    if ws == 1:
-        return [unpack_shard_records(mine, search_depth, row_cap)]
-    import torch
-    import torch.distributed as dist
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    t = torch.from_numpy(mine).to(dev)
-    out = torch.empty((ws * t.shape[0], t.shape[1]), dtype=t.dtype, device=dev)
-    dist.all_gather_into_tensor(out, t, group=group)
-    out = out.cpu().numpy().reshape(ws, t.shape[0], t.shape[1])
-    return [unpack_shard_records(out[s], search_depth, row_cap) for s in range(ws)]
+    gathered = _allgather_bytes(pack_shard_records(records, search_depth, row_cap), group)
+    return [unpack_shard_records(g) for g in gathered]
 
 
 def match_sharded(matcher, ht, queries, row_cap: int = 16, group=None):
     """Sharded-table match of `queries` (every rank passes the same list): this rank's
     device table must already be restricted to its id range
     (HashTable.restrict_device_ids(*id_range(nids, rank, world))).  Returns the rows a
-    single table gives, on every rank."""
+    single table gives, on every rank.  Per-query host objects (API convenience; the batch form
+    below is the throughput path)."""
     mine = matcher.match_batch_shard(ht, queries)
     shards = allgather_shard_records(mine, matcher.search_depth, row_cap, group)
     out = []
@@ -170,50 +184,49 @@ def match_sharded(matcher, ht, queries, row_cap: int = 16, group=None):
     return out
 
 
-# ---- vectorised form of the exchange for large query batches -------------------------
+# ---- vectorised host statement of pack / merge (tests; checks the device kernels) --------
 def pack_shard_batch(cand, counts, rows, row_off, row_cap: int) -> np.ndarray:
-    """Same record layout as pack_shard_records, built without a Python loop from the arrays
-    afp_fetch_match_candidates / afp_fetch_match_rows return:
-    cand (nq, sd, 3) f64, counts (nq, 2) i32 [entries, n_above], rows (R, 7) i32, row_off (nq+1)."""
+    """The wire records built without a Python loop from what afp_fetch_match_candidates /
+    afp_fetch_match_rows return: cand (nq, sd, 3) f64, counts (nq, 2) i32 [entries, n_above],
+    rows (R, 7) i32, row_off (nq+1)."""
     nq, sd = cand.shape[0], cand.shape[1]
     nrows = np.diff(row_off)
     if nq and nrows.max(initial=0) > row_cap:
         raise ValueError("a shard produced %d rows for one query, row_cap is %d" % (int(nrows.max()), row_cap))
-    out = np.zeros((nq, 3 + 3 * sd + 7 * row_cap), np.float64)
-    out[:, 0] = counts[:, 1]
-    out[:, 1] = counts[:, 0]
-    out[:, 2] = nrows
+    out = np.zeros(nq, record_dtype(sd, row_cap))
+    out["hdr"][:, 0], out["hdr"][:, 1], out["hdr"][:, 2] = counts[:, 1], counts[:, 0], nrows
     valid = np.arange(sd)[None, :] < counts[:, :1]
-    out[:, 3:3 + 3 * sd] = np.where(valid[:, :, None], cand, 0.0).reshape(nq, 3 * sd)
+    out["w"] = np.where(valid, cand[:, :, 2], 0.0)
+    out["id"] = np.where(valid, cand[:, :, 0], 0).astype(np.uint32)
+    out["raw"] = np.where(valid, cand[:, :, 1], 0).astype(np.uint32)
     if len(rows):
         q = np.repeat(np.arange(nq), nrows)
         k = np.arange(len(rows)) - np.repeat(row_off[:-1], nrows)
-        cols = 3 + 3 * sd + 7 * k[:, None] + np.arange(7)[None, :]
-        out[q[:, None], cols] = rows
+        out["rows"][q, k] = rows
     return out
 
 
-def merge_shard_batch(gathered: np.ndarray, search_depth: int, row_cap: int):
+def merge_shard_batch(gathered: np.ndarray, search_depth: int = None, row_cap: int = None):
     """Vectorised merge_sharded_results over a whole batch.
-    gathered: (S, nq, W) packed records of all shards.  Returns (rows (R,7) int32 in
+    gathered: (S, nq) structured records of all shards.  Returns (rows (R,7) int32 in
     (query, global rank) order, row_off (nq+1)).
 
     No sort of the merged candidate lists: only ids that produced rows need a global rank, and
     the rank of id x is the number of published candidates that order before it by (weight desc,
     id desc) - found by one bisection per (row, shard) in that shard's already ordered list."""
-    S, nq, _ = gathered.shape
-    sd = max(int(search_depth), 1)
-    depth = np.minimum(gathered[:, :, 0].sum(axis=0), search_depth).astype(np.int64)        # (nq,)
-    ncand = gathered[:, :, 1].astype(np.int64)                                               # (S, nq)
-    cand = gathered[:, :, 3:3 + 3 * sd].reshape(S, nq, sd, 3)
-    nrows = gathered[:, :, 2].astype(np.int64)                                               # (S, nq)
-    rows = gathered[:, :, 3 + 3 * sd:].reshape(S, nq, row_cap, 7)
-    s_idx, q_idx, k_idx = np.nonzero(np.arange(row_cap)[None, None, :] < nrows[:, :, None])
+    S, nq = gathered.shape
+    sd = gathered.dtype["w"].shape[0]
+    rcap = gathered.dtype["rows"].shape[0]
+    depth = np.minimum(gathered["hdr"][:, :, 0].sum(axis=0), sd if search_depth is None else search_depth).astype(np.int64)
+    ncand = gathered["hdr"][:, :, 1].astype(np.int64)                                         # (S, nq)
+    nrows = gathered["hdr"][:, :, 2].astype(np.int64)
+    W, I = gathered["w"], gathered["id"].astype(np.int64)                                      # (S, nq, sd)
+    s_idx, q_idx, k_idx = np.nonzero(np.arange(rcap)[None, None, :] < nrows[:, :, None])
     if len(q_idx) == 0:
         return np.zeros((0, 7), np.int32), np.zeros(nq + 1, np.int64)
-    r = rows[s_idx, q_idx, k_idx].astype(np.int64)                                            # (R0, 7)
-    w_x = cand[s_idx, q_idx, r[:, 4], 2][:, None]    # column 4 = rank in the shard's own list
-    i_x = r[:, :1].astype(np.float64)
+    r = gathered["rows"][s_idx, q_idx, k_idx].astype(np.int64)                                 # (R0, 7)
+    w_x = W[s_idx, q_idx, r[:, 4]][:, None]          # column 4 = rank in the shard's own list
+    i_x = r[:, :1]
     shard = np.arange(S)[None, :]
     lo = np.zeros((len(r), S), np.int64)
     hi = ncand[:, q_idx].T.copy()                                                             # (R0, S)
@@ -221,8 +234,8 @@ def merge_shard_batch(gathered: np.ndarray, search_depth: int, row_cap: int):
         active = lo < hi
         mid = (lo + hi) >> 1
         at = np.minimum(mid, sd - 1)
-        w = cand[shard, q_idx[:, None], at, 2]
-        before = (w > w_x) | ((w == w_x) & (cand[shard, q_idx[:, None], at, 0] > i_x))
+        w = W[shard, q_idx[:, None], at]
+        before = (w > w_x) | ((w == w_x) & (I[shard, q_idx[:, None], at] > i_x))
         lo = np.where(active & before, mid + 1, lo)
         hi = np.where(active & ~before, mid, hi)
     pos = lo.sum(axis=1)
@@ -236,23 +249,58 @@ def merge_shard_batch(gathered: np.ndarray, search_depth: int, row_cap: int):
     return r.astype(np.int32), np.cumsum(off)
 
 
-def match_sharded_batch(matcher, ht, packed_queries, row_cap: int = 16, group=None):
-    """Batch form of match_sharded: (query rows, offsets) in, (result rows, offsets) out, rows of
-    each query sorted by count descending (stable in global-rank order).  One all-gather."""
-    mine = matcher.match_batch_shard_packed(ht, packed_queries, row_cap)
+# ---- the product path: pack, all-gather and merge on the device -------------------------
+def match_sharded_batch(matcher, ht, packed_queries, row_cap: int = 16, group=None, fetch: bool = True):
+    """Sharded-table match of a packed (query rows, offsets) batch - every rank passes the same
+    batch, its device table restricted to its id range.  On the device: probe + rank the shard
+    (afp_match_batch, publish mode), pack one record per query (afp_shard_pack), ONE all-gather of
+    the record buffers (torch.distributed: NCCL device-to-device; under gloo the bytes take the
+    host route), merge (afp_shard_merge).  Returns (rows, offsets): the rows a single table gives,
+    in candidate-rank order per query (what Matcher.match_batch(sort=False) returns); with
+    fetch=False the result stays on the device (None, None)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    qrows, qoff = packed_queries
+    qrows = np.ascontiguousarray(qrows, dtype=np.int32).reshape(-1, 2)
+    qoff = np.ascontiguousarray(qoff, dtype=np.int64)
+    nq = len(qoff) - 1
+    sd = max(int(matcher.search_depth), 1)
+    p = matcher._params()
+    p.publish_candidates = 1
+    ctx = ht._sync_device()
+    matcher._run(ctx, p, qrows, nq, qoff)
+    rb = int(ctx.lib.afp_shard_record_bytes(sd, int(row_cap)))
+    if rb < 0:
+        raise ValueError("row_cap must be even and >= 2")
+    dev = torch.device("cuda", ctx.device)
+    mine = torch.empty((max(nq, 1), rb), dtype=torch.uint8, device=dev)
+    try:
+        ctx.check(ctx.lib.afp_shard_pack(ctx.h, int(row_cap), mine.data_ptr()))
+    except _lib.AfpError as e:
+        if "row capacity" in str(e):
+            raise ValueError("a shard produced more than row_cap=%d rows for one query" % row_cap)
+        raise
     rank, ws = world()
     if ws == 1:
-        gathered = mine[None]
+        gathered = mine
     else:
-        import torch
         import torch.distributed as dist
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
-            else torch.device("cpu")
-        t = torch.from_numpy(mine).to(dev)
-        out = torch.empty((ws * t.shape[0], t.shape[1]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(out, t, group=group)
-        gathered = out.cpu().numpy().reshape(ws, t.shape[0], t.shape[1])
-    rows, off = merge_shard_batch(gathered, matcher.search_depth, row_cap)
-    q = np.repeat(np.arange(len(off) - 1), np.diff(off))
-    o = np.lexsort((np.arange(len(rows)), -rows[:, 1].astype(np.int64), q))
-    return rows[o], off
+        if dist.get_backend(group) == "nccl":
+            gathered = torch.empty((ws * mine.shape[0], rb), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+        else:                                    # gloo: same bytes through host memory
+            h = mine.cpu()
+            g = torch.empty((ws * h.shape[0], rb), dtype=torch.uint8)
+            dist.all_gather_into_tensor(g, h, group=group)
+            gathered = g.to(dev)
+        torch.cuda.current_stream(dev).synchronize()
+    total = C.c_int64(0)
+    ctx.check(ctx.lib.afp_shard_merge(ctx.h, gathered.data_ptr(), ws, nq, sd, int(row_cap), C.byref(total)))
+    if not fetch:
+        return None, None
+    rows = np.empty((int(total.value), 7), np.int32)
+    roff = np.zeros(nq + 1, np.int64)
+    ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                           roff.ctypes.data_as(C.POINTER(C.c_int64))))
+    return rows, roff

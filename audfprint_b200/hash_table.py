@@ -20,6 +20,7 @@ import math
 import os
 import pickle
 import random
+import weakref
 
 import numpy as np
 
@@ -210,6 +211,103 @@ class HashTable(object):
         self.hashesperid[id_] += n
         self._touch()
 
+    # ---- batched insert on the device table ------------------------------
+    def store_batch(self, names, hashes=None):
+        """HashTable.store (hash_table.py:91-138) for a list of tracks in ONE device call.
+
+        names   track names, in insertion order
+        hashes  list of (time, hash) arrays, one per name - or None: the tracks are the files of the
+                last Analyzer device batch and their hashes are taken from the device workspace
+                without a round trip (Analyzer.ingest_batch)
+        The result is the table the reference builds by calling store() track by track from the
+        same `random` state: slots below `depth` are assigned on the device (rank of every entry
+        inside its bucket, in insertion order); entries that meet a full bucket come back in
+        order, `random.randint(0, count)` is replayed for them on a C copy of CPython's generator
+        (and `random`'s state advanced accordingly), and the winning writes return as patches.
+        Afterwards the DEVICE copy is the current one; `table` / `counts` refresh themselves from
+        it when read.  Returns the number of hashes stored per track."""
+        nfiles = len(names)
+        if nfiles == 0:
+            return []
+        ids = self._names_to_ids(names)
+        ctx = self._sync_device()                 # the device holds this table's current state
+        if self._shard is not None:
+            raise AfpStateError("the device copy is a shard (restrict_device_ids): cannot store into it")
+        nov = C.c_int64(0)
+        if hashes is None:
+            roff = np.empty(nfiles + 1, np.int64)
+            ctx.check(ctx.lib.afp_fetch_hashes(ctx.h, None, 1, roff.ctypes.data_as(C.POINTER(C.c_int64))))
+            ctx.check(ctx.lib.afp_table_store_batch(ctx.h, None, 0, None, nfiles, ids.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    C.byref(nov)))
+        else:
+            arrs = [np.asarray(h, dtype=np.int32).reshape(-1, 2) for h in hashes]
+            roff = np.zeros(nfiles + 1, np.int64)
+            roff[1:] = np.cumsum([len(a) for a in arrs])
+            rows = np.ascontiguousarray(np.concatenate(arrs)) if roff[-1] else np.zeros((0, 2), np.int32)
+            ctx.check(ctx.lib.afp_table_store_batch(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                                    roff.ctypes.data_as(C.POINTER(C.c_int64)), nfiles,
+                                                    ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nov)))
+        n = int(nov.value)
+        if n:
+            bucket, cnt, val = np.empty(n, np.uint32), np.empty(n, np.int32), np.empty(n, np.uint32)
+            ctx.check(ctx.lib.afp_table_fetch_overflow(ctx.h, bucket.ctypes.data, cnt.ctypes.data, val.ctypes.data))
+            st = random.getstate()
+            state = np.array(st[1], dtype=np.uint32)
+            slot = np.empty(n, np.int32)
+            ctx.check(ctx.lib.afp_mt_randint_replay(state.ctypes.data, cnt.ctypes.data, n, slot.ctypes.data))
+            random.setstate((st[0], tuple(int(x) for x in state), st[2]))
+            hit = np.nonzero((slot >= 0) & (slot < self.depth))[0]
+            if len(hit):
+                # several draws may name one slot: the last one in sequence wins (np.unique keeps the
+                # first occurrence, so look at the sequence backwards)
+                key = bucket[hit].astype(np.int64) * self.depth + slot[hit]
+                _, first_rev = np.unique(key[::-1], return_index=True)
+                keep = hit[len(hit) - 1 - first_rev]
+                b, sl, v = (np.ascontiguousarray(x[keep]) for x in (bucket, slot, val))
+                ctx.check(ctx.lib.afp_table_apply_patches(ctx.h, b.ctypes.data, sl.ctypes.data, v.ctypes.data, len(keep)))
+        per_track = np.diff(roff)
+        np.add.at(self.__dict__["_hashesperid"], ids, per_track.astype(np.uint32))
+        hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
+        ctx.check(ctx.lib.afp_table_set_hashesperid(ctx.h, hpi.ctypes.data if len(hpi) else None, len(hpi)))
+        self._touch()
+        self._dev_newer = True
+        ctx.table_key = self._stamp()             # the device copy IS this version
+        ctx.table_owner = weakref.ref(self)
+        return [int(x) for x in per_track]
+
+    def _names_to_ids(self, names):
+        """name_to_id(name, add_if_missing=True) (hash_table.py:325-345) for a list of names, without
+        the per-name list search: a known name keeps its id, a new one takes the first freed slot,
+        else the end of the list."""
+        known = {}
+        for i, n in enumerate(self.names):
+            if n is not None and n not in known:
+                known[n] = i
+        free = [i for i, n in enumerate(self.names) if n is None]
+        free.reverse()
+        ids = np.empty(len(names), np.int64)
+        hpi = self.__dict__["_hashesperid"]
+        grown = []
+        for k, name in enumerate(names):
+            if not isinstance(name, (str, bytes)):
+                ids[k] = name
+                continue
+            i = known.get(name)
+            if i is None:
+                if free:
+                    i = free.pop()
+                    self.names[i] = name
+                    hpi[i] = 0
+                else:
+                    i = len(self.names)
+                    self.names.append(name)
+                    grown.append(0)
+                known[name] = i
+            ids[k] = i
+        if grown:
+            self.hashesperid = np.concatenate([hpi, np.zeros(len(grown), np.uint32)]).astype(np.uint32)
+        return ids
+
     def get_entry(self, hash_):
         """int32 (n,2) [id, time] rows stored under one hash, from the host arrays
         (hash_table.py:140-148; the reference's own version trips over a misspelt attribute)."""
@@ -397,7 +495,12 @@ class HashTable(object):
             return ctx              # device copy is this table's shard
         if ctx.table_key != self._stamp():
             self._shard = None
-            table = np.ascontiguousarray(self.table, dtype=np.uint32)
+            # the device may hold ANOTHER table's only copy of its device-side inserts: save it first
+            owner = ctx.table_owner() if getattr(ctx, "table_owner", None) else None
+            if owner is not None and owner is not self and getattr(owner, "_dev_newer", False):
+                owner._pull_device()
+            ctx.table_owner = None
+            table = np.ascontiguousarray(self.table, dtype=np.uint32)     # (pulls the device copy first if it is newer)
             counts = np.ascontiguousarray(self.counts, dtype=np.int32)
             hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
             if table.shape != (1 << int(self.hashbits), int(self.depth)) or counts.shape != (1 << int(self.hashbits),):
@@ -423,7 +526,14 @@ class HashTable(object):
 
     def _pull_device(self):
         """Refresh the host arrays from the device copy after device-side inserts."""
-        raise AfpStateError("device copy is newer but no download path is built")
+        ctx = _lib.context(self.device)
+        if ctx.table_key != self._stamp():
+            raise AfpStateError("the device table that holds this table's inserts was replaced by another upload")
+        table = np.empty((1 << int(self.hashbits), int(self.depth)), np.uint32)
+        counts = np.empty(1 << int(self.hashbits), np.int32)
+        ctx.check(ctx.lib.afp_table_download(ctx.h, table.ctypes.data, counts.ctypes.data))
+        self.__dict__["_table"], self.__dict__["_counts"] = table, counts
+        self._dev_newer = False
 
     def get_hits(self, hashes):
         """[time, hash] rows -> int32 (nhits,4) [id, dtime, hash, time] rows in

@@ -106,12 +106,23 @@ class Matcher(object):
         roff = np.zeros(nq + 1, np.int64)
         ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                roff.ctypes.data_as(C.POINTER(C.c_int64))))
-        out = []
-        for i in range(nq):
+        if sort and len(rows):
+            rows = self._sort_by_count(rows, roff)
+        return [rows[roff[i]:roff[i + 1]] for i in range(nq)]
+
+    @staticmethod
+    def _sort_by_count(rows, roff):
+        """`results[(-results[:, 1]).argsort(),]` (audfprint_match.py:335) for every query of a batch.
+        One vectorised pass orders all queries by count descending; only where a query has EQUAL
+        counts (the reference's argsort is unstable, so their order is whatever NumPy does on this
+        machine) is that query re-ordered with the reference's own per-query call."""
+        q = np.repeat(np.arange(len(roff) - 1), np.diff(roff))
+        order = np.lexsort((-rows[:, 1].astype(np.int64), q))
+        out = rows[order]
+        tied = np.nonzero((q[order][1:] == q[order][:-1]) & (out[1:, 1] == out[:-1, 1]))[0]
+        for i in np.unique(q[order][tied]):
             r = rows[roff[i]:roff[i + 1]]
-            if sort:
-                r = r[(-r[:, 1]).argsort(), ]        # audfprint_match.py:335
-            out.append(r)
+            out[roff[i]:roff[i + 1]] = r[(-r[:, 1]).argsort(), ]
         return out
 
     # ---- exact_count / find_time_range / hashesfor (audfprint_match.py:149-244) ----

@@ -180,6 +180,34 @@ int afp_sgram(afp_ctx* ctx, const void* pcm, int pcm_dtype, int pcm_on_host, int
 int afp_table_upload(afp_ctx* ctx, const uint32_t* table, const int32_t* counts,
                      int32_t hashbits, int32_t depth, int32_t maxtimebits,
                      const uint32_t* hashesperid, int64_t nids, int on_host);
+/* An empty device table (HashTable.__init__ / reset, hash_table.py:59-89). */
+int afp_table_create(afp_ctx* ctx, int32_t hashbits, int32_t depth, int32_t maxtimebits);
+/* Replace the device copy of hashesperid (host bookkeeping after store / remove). */
+int afp_table_set_hashesperid(afp_ctx* ctx, const uint32_t* hashesperid, int64_t nids);
+/* HashTable.store (hash_table.py:91-138) for a batch of tracks, on the device table:
+ *   rows         int32 [M][2] (time, hash), the files' rows one after the other; NULL = the
+ *                hashes of the last afp_fingerprint_batch, taken from the workspace in place
+ *   row_offsets  HOST int64 [nfiles+1] (ignored with rows = NULL)
+ *   ids          HOST int64 [nfiles] track id of every file (HashTable.name_to_id)
+ * Entries that land below `depth` are written (same slots as the reference's sequential loop);
+ * entries that hit a full bucket are NOT applied: *noverflow of them wait, in sequence order,
+ * for afp_table_fetch_overflow -> (bucket, count before the insert, value).  The reference draws
+ * random.randint(0, count) for each of those and writes slot < depth (hash_table.py:127-134): the
+ * caller replays the draws (afp_mt_randint_replay) and returns the writes with
+ * afp_table_apply_patches (later patches of one slot win, as in the sequential loop: the caller
+ * passes one patch per slot). */
+int afp_table_store_batch(afp_ctx* ctx, const int32_t* rows, int rows_on_host, const int64_t* row_offsets,
+                          int32_t nfiles, const int64_t* ids, int64_t* noverflow);
+int afp_table_fetch_overflow(afp_ctx* ctx, uint32_t* bucket, int32_t* count_before, uint32_t* value);
+int afp_table_apply_patches(afp_ctx* ctx, const uint32_t* bucket, const int32_t* slot, const uint32_t* value,
+                            int64_t n);
+/* Copy the device table back: table uint32 [2^hashbits][depth], counts int32 [2^hashbits] (HOST). */
+int afp_table_download(afp_ctx* ctx, uint32_t* table, int32_t* counts);
+/* CPython's `random.randint(0, count)` replayed for n draws.  state625 = the 625 uint32 of
+ * random.getstate()[1] (MT19937 words + position), updated in place so that
+ * random.setstate() continues where the reference would.  Host arithmetic only: this is the
+ * reference's RNG, not part of the hot path. */
+int afp_mt_randint_replay(uint32_t* state625, const int32_t* count_before, int64_t n, int32_t* slot_out);
 /* Keep only ids in [id_lo, id_hi) of the uploaded table (sharded table,
  * SURVEY.md §8e); bucket-slot order is preserved. */
 int afp_table_restrict_ids(afp_ctx* ctx, int64_t id_lo, int64_t id_hi);
@@ -218,6 +246,21 @@ int afp_fetch_match_status(afp_ctx* ctx, int32_t* status);
  * [nqueries][search_depth][3] = (id, raw count, weighted count) in (weight desc, id desc)
  * order, `counts` int32 [nqueries][2] = (entries used, #ids with raw > threshcount). */
 int afp_fetch_match_candidates(afp_ctx* ctx, double* cand, int32_t* counts, int on_host);
+
+/* ---- table sharded by track-id range (BASELINE configs[4]) -----------------
+ * The reference has no such mode; the nearest thing is one table per worker process merged
+ * afterwards (audfprint.py:199-235, hash_table.py:291-323).  Every rank uploads the table,
+ * keeps its id range (afp_table_restrict_ids), runs afp_match_batch with publish_candidates = 1
+ * on ALL queries, packs one fixed-size record per query into a caller-owned DEVICE buffer, the
+ * caller all-gathers the buffers (NCCL), and afp_shard_merge rebuilds on the device the rows a
+ * single table would give (same rows, same ranks); fetch them with afp_fetch_match_rows.
+ * Record (little endian): int32 {n_above, ncand, nrows, 0}; f64 weight[sd]; uint32 id[sd];
+ * uint32 raw[sd]; int32 rows[row_cap][7].  row_cap must be even. */
+int64_t afp_shard_record_bytes(int32_t search_depth, int32_t row_cap);
+int afp_shard_pack(afp_ctx* ctx, int32_t row_cap, void* records_dev /* [nqueries][record bytes] */);
+int afp_shard_merge(afp_ctx* ctx, const void* gathered_dev /* [nshards][nqueries][record bytes] */,
+                    int32_t nshards, int32_t nqueries, int32_t search_depth, int32_t row_cap,
+                    int64_t* total_rows);
 
 #ifdef __cplusplus
 }

@@ -334,7 +334,8 @@ def test_table_shards_publish_and_merge(golden_match, db, nshards):
 
 
 def test_shard_batch_path_single_rank(golden_match):
-    """world_size 1: match_sharded_batch (packed records, vectorised merge) == match_batch."""
+    """world_size 1: match_sharded_batch (device pack + device merge of one shard) == match_batch,
+    rank order and ranks included."""
     from audfprint_b200 import dist as afd
     gm = golden_match
     table, counts, hashbits, depth, mtb, hpi = expand_table(gm, "db2")
@@ -349,8 +350,62 @@ def test_shard_batch_path_single_rank(golden_match):
     rows, off = afd.match_sharded_batch(m, ht, (np.concatenate(qs), qoff), row_cap=64)
     single = m.match_batch(ht, qs, sort=False)
     for i, s in enumerate(single):
-        want = s[np.argsort(-s[:, 1], kind="stable")]
-        assert np.array_equal(rows[off[i]:off[i + 1]], want)
+        assert np.array_equal(rows[off[i]:off[i + 1]], s), keys[i]
+    with pytest.raises(ValueError):
+        afd.match_sharded_batch(m, ht, (np.concatenate(qs), qoff), row_cap=2)     # a query has more rows
+
+
+@pytest.mark.parametrize("db,nshards,force_general", [("db", 2, False), ("db2", 3, False), ("db2", 5, True)])
+def test_device_pack_and_merge_equal_the_host_statement(golden_match, db, nshards, force_general):
+    """afp_shard_pack / afp_shard_merge (the kernels of the sharded-table exchange) against the
+    NumPy statement of the same record format and merge (audfprint_b200/dist.py), and the merged
+    rows against the single table - the shards are visited one after the other on one GPU and their
+    record buffers stacked exactly as an all-gather would deliver them."""
+    import ctypes as C
+    import torch
+    from audfprint_b200 import dist as afd
+    gm = golden_match
+    table, counts, hashbits, depth, mtb, hpi = expand_table(gm, db)
+    ht = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpi
+    keys = ["q%d_%s" % (j, tag) for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+    qs = [gm[k + "/q"] for k in keys] + [np.zeros((0, 2), np.int32)]
+    qoff = np.zeros(len(qs) + 1, np.int64)
+    qoff[1:] = np.cumsum([len(q) for q in qs])
+    packed = np.ascontiguousarray(np.concatenate(qs))
+    nq, rcap = len(qs), 64
+    m = Matcher()
+    m.window, m.threshcount, m.search_depth = 2, 5, 100
+    m.force_general_kernel = force_general
+    single = m.match_batch(ht, qs, sort=False)
+    ctx = ht._sync_device()
+    rb = int(ctx.lib.afp_shard_record_bytes(m.search_depth, rcap))
+    assert rb == afd.record_dtype(m.search_depth, rcap).itemsize
+    bufs, host = [], []
+    for s in range(nshards):
+        lo, hi = afd.id_range(len(hpi), s, nshards)
+        ht.restrict_device_ids(lo, hi)
+        rows, roff, cand, cnts = m._publish_call(ht, packed, qoff)
+        host.append(afd.pack_shard_batch(cand, cnts, rows, roff, rcap))
+        buf = torch.empty((nq, rb), dtype=torch.uint8, device="cuda")
+        ctx.check(ctx.lib.afp_shard_pack(ctx.h, rcap, buf.data_ptr()))
+        got = buf.cpu().numpy().view(host[-1].dtype).reshape(nq)
+        for f in ("hdr", "id", "raw", "rows"):
+            assert np.array_equal(got[f], host[-1][f]), (s, f)
+        assert np.array_equal(got["w"], host[-1]["w"])
+        bufs.append(buf)
+    ht._touch()
+    gathered = torch.cat(bufs, dim=0)
+    total = C.c_int64(0)
+    ctx.check(ctx.lib.afp_shard_merge(ctx.h, gathered.data_ptr(), nshards, nq, m.search_depth, rcap, C.byref(total)))
+    rows = np.empty((int(total.value), 7), np.int32)
+    roff = np.zeros(nq + 1, np.int64)
+    ctx.check(ctx.lib.afp_fetch_match_rows(ctx.h, rows.ctypes.data if len(rows) else None, 1,
+                                           roff.ctypes.data_as(C.POINTER(C.c_int64))))
+    want_rows, want_off = afd.merge_shard_batch(np.stack(host), m.search_depth, rcap)
+    assert np.array_equal(roff, want_off) and np.array_equal(rows, want_rows)
+    for i, s in enumerate(single):
+        assert np.array_equal(rows[roff[i]:roff[i + 1]], s), (db, keys[i] if i < len(keys) else "empty")
 
 
 @pytest.mark.parametrize("density,fanout,shifts,f_sd,maxpks", [
