@@ -147,7 +147,7 @@ class HashTable(object):
         if getattr(self, "_dev_newer", False):
             self._pull_device()
         st = dict(self.__dict__)
-        for k in ("_token", "_version", "_dev_newer", "_shard"):
+        for k in ("_token", "_version", "_dev_newer", "_shard", "_dev_key"):
             st.pop(k, None)
         for k in ("table", "counts", "hashesperid"):      # the reference's attribute names
             st[k] = st.pop("_" + k)
@@ -229,10 +229,10 @@ class HashTable(object):
         nfiles = len(names)
         if nfiles == 0:
             return []
-        ids = self._names_to_ids(names)
-        ctx = self._sync_device()                 # the device holds this table's current state
         if self._shard is not None:
             raise AfpStateError("the device copy is a shard (restrict_device_ids): cannot store into it")
+        ctx = self._sync_device()                 # the device holds this table's current state
+        ids = self._names_to_ids(names)           # (host bookkeeping; the device copy stays the current one)
         nov = C.c_int64(0)
         if hashes is None:
             roff = np.empty(nfiles + 1, np.int64)
@@ -271,7 +271,7 @@ class HashTable(object):
         ctx.check(ctx.lib.afp_table_set_hashesperid(ctx.h, hpi.ctypes.data if len(hpi) else None, len(hpi)))
         self._touch()
         self._dev_newer = True
-        ctx.table_key = self._stamp()             # the device copy IS this version
+        ctx.table_key = self._dev_key = self._stamp()      # the device copy IS this version
         ctx.table_owner = weakref.ref(self)
         return [int(x) for x in per_track]
 
@@ -527,7 +527,7 @@ class HashTable(object):
     def _pull_device(self):
         """Refresh the host arrays from the device copy after device-side inserts."""
         ctx = _lib.context(self.device)
-        if ctx.table_key != self._stamp():
+        if ctx.table_key != getattr(self, "_dev_key", None):
             raise AfpStateError("the device table that holds this table's inserts was replaced by another upload")
         table = np.empty((1 << int(self.hashbits), int(self.depth)), np.uint32)
         counts = np.empty(1 << int(self.hashbits), np.int32)

@@ -82,17 +82,69 @@ def make_tracks(pool, first_seed, nfiles, secs):
 _TRACKS = None      # set before the CPU pool is forked: workers inherit the PCM, tasks are indices
 
 
+def reference_dir():
+    """A checkout of the reference (dpwe/audfprint) if one is reachable: $AFP_REFERENCE,
+    baseline/_ref, /root/reference.  It is pure Python and is NOT part of this repo, so on the
+    GPU box there is normally none and the CPU arm is the oracle port (`kind: "port"`)."""
+    for d in (os.environ.get("AFP_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if d and os.path.isfile(os.path.join(d, "audfprint_analyze.py")):
+            return d
+    return None
+
+
+_REF_MOD = None
+
+
 def _worker_init():
     # pay the (cold-container) import cost before anything is timed
+    global _REF_MOD
     import scipy.signal  # noqa: F401
     from oracle import afp_oracle  # noqa: F401
     from audfprint_b200 import synth  # noqa: F401
+    d = reference_dir()
+    if d:
+        sys.path.insert(0, d)
+        try:
+            import audfprint_analyze as ref_an       # the unmodified reference
+            _REF_MOD = ref_an
+        except Exception:
+            _REF_MOD = None
 
 
 def _cpu_fp(i):
-    from oracle import afp_oracle as orc
     from audfprint_b200.synth import pcm_to_float
-    return orc.fingerprint(pcm_to_float(_TRACKS[i]), density=20.0, fanout=3, shifts=1)
+    d = pcm_to_float(_TRACKS[i])
+    if _REF_MOD is not None:
+        # Analyzer.wavfile2hashes minus the file read (audfprint_analyze.py:385-426, shifts = 1):
+        # the reference's own find_peaks / peaks2landmarks / landmarks2hashes
+        an = _REF_MOD.Analyzer(20.0)
+        return np.asarray(_REF_MOD.landmarks2hashes(an.peaks2landmarks(an.find_peaks(d, SR))), np.int32).reshape(-1, 2)
+    from oracle import afp_oracle as orc
+    return orc.fingerprint(d, density=20.0, fanout=3, shifts=1)
+
+
+def cpu_kind():
+    return "reference" if reference_dir() else "port"
+
+
+def config0_single_core(seed=0, secs=60.0, reps=5):
+    """BASELINE configs[0]: one 60 s clip, single core, median of `reps` (the reference's own
+    CPU path when a checkout is reachable, else the oracle port)."""
+    global _TRACKS
+    from audfprint_b200.synth import synth_track
+    saved = _TRACKS
+    _TRACKS = [synth_track(seed, secs)]
+    _worker_init()
+    _cpu_fp(0)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        h = _cpu_fp(0)
+        ts.append(time.perf_counter() - t0)
+    _TRACKS = saved
+    return {"workload": "Analyzer.wavfile2hashes on one %g s 11025 Hz mono clip (BASELINE configs[0])" % secs,
+            "kind": cpu_kind(), "cores": 1, "median_s": float(np.median(ts)), "runs": reps,
+            "audio_s_per_s": secs / float(np.median(ts)), "hashes": int(len(h))}
 
 
 def cpu_pool(tracks, nproc):
@@ -338,9 +390,10 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
 
 
 def bench_match_sharded(a, an, rows, roff, queries, rank, world):
-    """BASELINE configs[4]: the 2^20 x 100 table sharded by track-id range over the ranks;
-    every rank probes its shard for ALL queries, ONE NCCL all-gather of fixed-size per-query
-    records (local top-search_depth candidates + rows), identical merge on every rank."""
+    """BASELINE configs[4]: the 2^20 x 100 table sharded by track-id range over the ranks; every
+    rank probes its shard for ALL queries (K4 in publish mode), packs one record per query on the
+    device, ONE NCCL all-gather of the record buffers, and merges on the device
+    (afp_shard_pack / afp_shard_merge).  Queries go through in batches of --match-batch."""
     import torch
     import torch.distributed as dist
     from audfprint_b200 import Analyzer, HashTable, Matcher
@@ -354,17 +407,24 @@ def bench_match_sharded(a, an, rows, roff, queries, rank, world):
     qan = Analyzer(device=an.device)
     qan.shifts = 4
     qh = qan.fingerprint_batch([q[0] for q in queries])
-    qoff = np.zeros(len(qh) + 1, np.int64)
-    qoff[1:] = np.cumsum([len(h) for h in qh])
-    qrows = np.ascontiguousarray(np.concatenate(qh))
+    nq = len(qh)
+    B = max(1, min(a.match_batch, nq))
+    batches = []
+    for b0 in range(0, nq, B):
+        part = qh[b0:b0 + B]
+        off = np.zeros(len(part) + 1, np.int64)
+        off[1:] = np.cumsum([len(h) for h in part])
+        batches.append((np.ascontiguousarray(np.concatenate(part)), off))
     m = Matcher()
     m.window = 2
     full = None
     if rank == 0:                                                # single-table answer for the parity check
-        full = m.match_batch(ht, (qrows, qoff), sort=False)
+        full = []
+        for qb in batches:
+            full += m.match_batch(ht, qb, sort=False)
     # ---- replicated table, queries sharded j % world (no collective): the fast layout when
     # the table fits one GPU (419 MB << 180 GB), SURVEY.md 8e
-    mine = afd.shard_indices(len(qh), rank, world)
+    mine = afd.shard_indices(nq, rank, world)
     my_rows = np.ascontiguousarray(np.concatenate([qh[i] for i in mine])) if len(mine) else np.zeros((0, 2), np.int32)
     my_off = np.zeros(len(mine) + 1, np.int64)
     my_off[1:] = np.cumsum([len(qh[i]) for i in mine])
@@ -381,36 +441,185 @@ def bench_match_sharded(a, an, rows, roff, queries, rank, world):
     rep_bad = 0
     if rank == 0:
         rep_bad = sum(0 if np.array_equal(rep[k], full[i]) else 1 for k, i in enumerate(mine))
+    # ---- sharded table
     lo, hi = afd.id_range(a.match_ids, rank, world)
     ht.restrict_device_ids(lo, hi)
+    res = None
     for _ in range(2):
-        res, off = afd.match_sharded_batch(m, ht, (qrows, qoff), row_cap=16)
+        for qb in batches[:2]:
+            afd.match_sharded_batch(m, ht, qb, row_cap=16, fetch=False)
     steps = 3
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res, off = afd.match_sharded_batch(m, ht, (qrows, qoff), row_cap=16)
+        for qb in batches:
+            afd.match_sharded_batch(m, ht, qb, row_cap=16, fetch=False)      # merged rows stay on the device
     torch.cuda.synchronize()
     dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    st = Matcher.last_status(ht, len(batches[-1][1]) - 1)
+    dist.barrier()
+    t0 = time.perf_counter()
+    res = [afd.match_sharded_batch(m, ht, qb, row_cap=16) for qb in batches]   # host hashes in, rows out
+    torch.cuda.synchronize()
+    dte = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dte, op=dist.ReduceOp.MAX)
     out = None
     if rank == 0:
-        bad = 0
-        for i, s in enumerate(full):
-            want = s[np.argsort(-s[:, 1], kind="stable")]
-            bad += 0 if np.array_equal(res[off[i]:off[i + 1]], want) else 1
-        nq = len(qh)
+        bad, k = 0, 0
+        for rws, off in res:                    # rank-order rows, ranks included: no sort on either side
+            for i in range(len(off) - 1):
+                bad += 0 if np.array_equal(rws[off[i]:off[i + 1]], full[k]) else 1
+                k += 1
+        rb = 16 + 16 * 100 + 28 * 16
         out = {"metric": "match_queries_per_sec", "queries": nq, "value": nq / float(dt[0]), "unit": "queries/s",
                "ms_per_step": float(dt[0]) * 1e3,
-               "parallelism": "table sharded by track-id range x%d; every rank probes all queries; one NCCL "
-                              "all-gather of %d-byte per-query records per batch" % (world, 8 * (3 + 300 + 7 * 16)),
-               "timing": "host wall clock around probe + all-gather + merge, max over ranks (host hashes in, rows out)",
-               "parity": {"queries_checked": nq, "queries_mismatched_vs_single_table": bad},
+               "parallelism": "table sharded by track-id range x%d; every rank probes all queries; device pack, one "
+                              "NCCL all-gather of %d-byte per-query records per batch of %d queries, device merge"
+                              % (world, rb, B),
+               "timing": "host wall clock around probe + pack + all-gather + merge with the merged rows left on the "
+                         "device, max over ranks (every call ends with a stream synchronise)",
+               "e2e": {"value": nq / float(dte[0]), "unit": "queries/s",
+                       "h2d_bytes_per_step": int(sum(b[0].nbytes + b[1].nbytes for b in batches)),
+                       "d2h_bytes_per_step": int(sum(r[0].nbytes + r[1].nbytes for r in res))},
+               "allgather_bytes_per_rank_per_step": int(nq * rb),
+               "fast_kernel_last_batch": {"queries_on_fast_kernel": int(np.sum(st[:, 0] == 0)),
+                                          "handed_to_general_kernel": int(np.sum(st[:, 0] > 0)),
+                                          "mean_multi_record_ids": float(st[:, 1].mean()),
+                                          "mean_single_record_ids_admitted": float(st[:, 3].mean())},
+               "parity": {"queries_checked": nq, "queries_mismatched_vs_single_table": bad,
+                          "compared": "rows in candidate-rank order incl. the rank column, exact"},
                "replicated_table": {"value": nq / float(dtr[0]), "unit": "queries/s", "ms_per_step": float(dtr[0]) * 1e3,
                                     "parallelism": "table replicated, queries sharded j %% %d, no collective" % world,
                                     "parity": {"queries_checked": len(mine), "queries_mismatched": rep_bad}}}
     return out
+
+
+# ---------------------------------------------------------------- ingest (BASELINE configs[3])
+def bench_ingest(a, rank, local_rank, world, cores, pool):
+    """BASELINE configs[3]: ingest 180 s tracks, file-sharded over the ranks (track i -> rank
+    i % world as audfprint.py:211-214 deals files), density 20, fanout 3, 5 peaks/frame, into a
+    per-rank device-resident 2^20 x 100 table with maxtimebits 14: a step = one batch of --files
+    tracks through Analyzer.fingerprint_packed + HashTable.store_batch (fingerprint AND store).
+    The PCM comes from a recycled pool of --files distinct seeded tracks; every step stores them
+    under new names, so the table fills (and overflows) as a real ingest does."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from audfprint_b200 import Analyzer, HashTable, _lib
+    nsamp = int(round(a.seconds * SR))
+    tracks = make_tracks(pool, 10 ** 6 + rank * a.files, a.files, a.seconds)
+    pool.close()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stride = (nsamp + 7) // 8 * 8
+    host_pcm = torch.zeros(a.files * stride + 8, dtype=torch.int16).pin_memory()
+    hp = host_pcm.numpy()
+    for i, t in enumerate(tracks):
+        hp[i * stride:i * stride + nsamp] = t
+    offs = np.arange(a.files + 1, dtype=np.int64) * stride
+    lens = np.full(a.files, nsamp, np.int64)
+    dev_pcm = host_pcm.cuda()
+    an = Analyzer(device=local_rank)
+    ctx = _lib.context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    random.seed(1000 + rank)
+    ht = HashTable(hashbits=20, depth=100, maxtime=1 << 14, device=local_rank)
+    audio_s = a.files * a.seconds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k, pcm):
+        an.fingerprint_packed(pcm, offs, fetch=False, sample_lengths=lens)
+        return ht.store_batch(["r%d/s%d/t%d" % (rank, k, i) for i in range(a.files)])
+
+    # parity of the first batch against the host store() (pinned to the reference), rank 0
+    parity = None
+    warm = max(a.warmup, 1)
+    counts0 = step(-1, dev_pcm)
+    if rank == 0:
+        rows, roff = an.fingerprint_packed(dev_pcm, offs, sample_lengths=lens)
+        random.seed(1000)
+        ref = HashTable(hashbits=20, depth=100, maxtime=1 << 14, device=local_rank)
+        for i in range(a.files):
+            ref.store("x%d" % i, rows[roff[i]:roff[i + 1]])
+        same = bool(np.array_equal(ref.counts, ht.counts) and np.array_equal(ref.table, ht.table))
+        parity = {"what": "device store_batch of the first %d tracks vs the host store() of the same hashes "
+                          "(bit-compatible with the reference's HashTable.store)" % a.files,
+                  "tables_identical": same, "hashes": int(sum(counts0))}
+    for k in range(1, warm):
+        step(-1 - k, dev_pcm)
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fp_ms, k1_ms = 0.0, 0.0
+    e0.record(stream)
+    for k in range(a.steps):
+        step(k, dev_pcm)
+        st_ms = ctx.stage_ms()
+        fp_ms += sum(st_ms[1:])
+        k1_ms += st_ms[1]
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    ctx.set_profiling(False)
+    ntracks = len(ht.names)
+    # end to end: pinned host PCM in every step
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        step(1000 + k, hp)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    nh = int(np.sum(ht.hashesperid))
+    full = float(np.mean(np.minimum(ht.counts, ht.depth))) / ht.depth
+    dropped = 1.0 - float(np.sum(np.minimum(ht.counts, ht.depth))) / max(1, int(np.sum(ht.counts)))
+    if rank == 0:
+        peak, which = measured_peaks()
+        T = 1 + nsamp // 256
+        k1_bytes = a.files * (2 * nsamp + 8 * 256 * T + 8 * T)
+        val = audio_s * world * a.steps / (ms_total * 1e-3)
+        out = {"metric": "audio_seconds_ingested_per_sec", "value": val, "unit": UNIT, "n_gpus": world,
+               "steps": a.steps, "warmup": warm, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "ingest %d x %g s synthetic tracks per GPU per step, file-sharded x%d "
+                                      "(BASELINE configs[3]: 100k x 180 s over 8 GPUs = %d steps of 1024 per GPU), "
+                                      "fingerprint + HashTable.store on the device, table 2^20 x 100, maxtimebits 14"
+                                      % (a.files, a.seconds, world, 12),
+                          "files_per_gpu_per_step": a.files, "seconds_per_file": a.seconds, "density": 20,
+                          "fanout": 3, "pks_per_frame": 5, "tracks_ingested_per_gpu": ntracks,
+                          "cache": "inputs larger than L2", "parallelism": "file-sharded x%d, no collective" % world},
+               "clocks": clocks,
+               "e2e": {"value": audio_s * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(hp.nbytes + offs.nbytes + lens.nbytes), "d2h_bytes_per_step": int(offs.nbytes),
+                       "ms_per_step": e2e_ms / a.steps},
+               "gpu_launches": int(launches),
+               "split_ms_per_step": {"fingerprint_kernels": fp_ms / a.steps, "store_and_host": ms_total / a.steps - fp_ms / a.steps},
+               "roofline": {"kernel": "afp_stft_kernel<int16> (K1)", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                            "peak_source": which, "algorithmic_bytes_per_launch": k1_bytes, "traffic": None,
+                            "launch_ms": k1_ms / a.steps, "achieved": k1_bytes / (k1_ms / a.steps * 1e-3) / 1e9,
+                            "frac": k1_bytes / (k1_ms / a.steps * 1e-3) / 1e9 / peak},
+               "table": {"tracks": ntracks, "hashes_stored_or_dropped": nh, "bucket_fill": full, "dropped_fraction": dropped},
+               "parity": parity, "cpu_baseline": None}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 def measured_peaks():
@@ -433,11 +642,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling aid: run only the device-resident timed region (e2e = null)")
-    ap.add_argument("--match-queries", type=int, default=4096,
-                    help="queries of the match workload (0 = skip; BASELINE configs[2] uses 10000)")
+    ap.add_argument("--match-queries", type=int, default=None,
+                    help="queries of the match workload (0 = skip; default 10000 = BASELINE configs[2]; "
+                         "100000 with --config 4)")
     ap.add_argument("--match-ids", type=int, default=1000000)
+    ap.add_argument("--match-batch", type=int, default=10000, help="queries per device call of the sharded match")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs[]: 1 batch fingerprint (default; the driver's line), 2 match 10k "
+                         "queries on 1 GPU, 3 ingest 180 s tracks incl. store, 4 sharded-table match of 100k queries")
     ap.add_argument("--match-cpu-sample", type=int, default=128)
     a = ap.parse_args()
+    if a.match_queries is None:
+        a.match_queries = 100000 if a.config == 4 else 10000
+    if a.config == 3:
+        a.seconds = 180.0 if a.seconds == 30.0 else a.seconds
+        a.steps = 12 if a.steps == 10 else a.steps
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -474,18 +693,24 @@ def main():
             times.append(dt)
         tot = sum(times)
         val = per_step * a.seconds * a.steps / tot
-        sample = "%d of the %d files per step, oracle port (NumPy/SciPy, same call structure as the " \
-                 "reference) over a %d-process pool" % (per_step, a.files, cores)
+        kind = cpu_kind()
+        sample = "%d of the %d files per step, %s over a %d-process pool (affinity/cgroup-limited: %s)" % (
+            per_step, a.files, "the unmodified reference (find_peaks/peaks2landmarks/landmarks2hashes)"
+            if kind == "reference" else "oracle port (NumPy/SciPy, same call structure as the reference)",
+            cores, cores_info)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                           "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                           "sample": sample, "host_cores": cores_info},
+                          "config0": config0_single_core(),
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
     # ------------------------------------------------------------ our arm
+    if a.config == 3:
+        return bench_ingest(a, rank, local_rank, world, cores, pool)
     tracks = make_tracks(pool, rank * a.files, a.files, a.seconds)
     do_match = a.match_queries > 0
     queries = None
@@ -625,9 +850,11 @@ def main():
         bad = sum(0 if np.array_equal(rows[roff[i]:roff[i + 1]], want[i]) else 1 for i in range(ns))
         parity = {"files_checked": ns, "files_mismatched": bad,
                   "hashes_checked": int(sum(len(w) for w in want))}
-        cpu = {"value": ns * a.seconds / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d of the %d files (%.0f audio-s), oracle port on a %d-process pool, %.1f s wall"
-                         % (ns, a.files, ns * a.seconds, cores, dt)}
+        cpu = {"value": ns * a.seconds / dt, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+               "host_cores": cores_info,
+               "sample": "%d of the %d files (%.0f audio-s), %s on a %d-process pool, %.1f s wall"
+                         % (ns, a.files, ns * a.seconds, "reference" if cpu_kind() == "reference" else "oracle port",
+                            cores, dt)}
 
     match = None
     if do_match and world == 1:
@@ -666,7 +893,23 @@ def main():
                              "k3_hashes": float(stages[4])},
                "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity, "match": match,
                "fp32_mode": fp32}
-        print(json.dumps(out))
+        if a.config in (2, 4) and match is not None:
+            # BASELINE configs[2] / configs[4]: the match leg is the headline line, the fingerprint
+            # numbers of the same run ride along
+            line = dict(match)
+            line.update({"n_gpus": world, "steps": 3 if world > 1 else 5, "warmup": 2, "higher_is_better": True,
+                         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32",
+                         "data": "synthetic", "clocks": clocks, "gpu_launches": 2,
+                         "config": {"workload": ("match %d x 10 s noisy synthetic queries (4 shifts) against a "
+                                                 "%d-track device-resident HashTable 2^20 x 100 (BASELINE configs[%d])"
+                                                 % (a.match_queries, a.match_ids, a.config)) +
+                                    (", table sharded by id range x%d, one NCCL all-gather per batch" % world
+                                     if world > 1 else ""),
+                                    "cache": "419 MB table + per-query scratch larger than L2 in aggregate"},
+                         "fingerprint_leg": {k: out[k] for k in ("value", "unit", "ms_per_step", "stages_ms")}})
+            print(json.dumps(line))
+        else:
+            print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     if cpool:

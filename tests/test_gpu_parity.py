@@ -352,7 +352,7 @@ def test_shard_batch_path_single_rank(golden_match):
     for i, s in enumerate(single):
         assert np.array_equal(rows[off[i]:off[i + 1]], s), keys[i]
     with pytest.raises(ValueError):
-        afd.match_sharded_batch(m, ht, (np.concatenate(qs), qoff), row_cap=2)     # a query has more rows
+        afd.match_sharded_batch(m, ht, (np.concatenate(qs), qoff), row_cap=3)     # must be even
 
 
 @pytest.mark.parametrize("db,nshards,force_general", [("db", 2, False), ("db2", 3, False), ("db2", 5, True)])
