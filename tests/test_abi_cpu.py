@@ -219,25 +219,6 @@ def test_table_bookkeeping_equals_the_reference(golden_match, capsys):
     assert ht.names[3] == "late" and "Removed track3 ( 335 hashes)." in capsys.readouterr().out
 
 
-def test_wav_reader_downmixes_and_resamples(tmp_path):
-    """The stand-in for audio_read: stereo 22050 Hz in -> mono float32 at the analyzer's rate."""
-    import wave
-    fs, secs, f0 = 22050, 2.0, 1000.0
-    t = np.arange(int(fs * secs)) / fs
-    left = (0.5 * np.sin(2 * np.pi * f0 * t) * 32767).astype("<i2")
-    stereo = np.stack([left, left], axis=1)
-    fn = str(tmp_path / "s.wav")
-    with wave.open(fn, "wb") as w:
-        w.setnchannels(2); w.setsampwidth(2); w.setframerate(fs)
-        w.writeframes(stereo.tobytes())
-    d, sr = an_mod._wav_reader(fn, sr=11025, channels=1)
-    assert sr == 11025 and d.dtype == np.float32 and abs(len(d) - 11025 * secs) <= 1
-    spec = np.abs(np.fft.rfft(d[1000:9192]))
-    assert abs(np.argmax(spec) * 11025 / 8192 - f0) < 2.0 and abs(np.max(np.abs(d[500:-500])) - 0.5) < 0.01
-    d2, sr2 = an_mod._wav_reader(fn)                      # no target rate: native rate, still mono
-    assert sr2 == fs and len(d2) == len(left)
-
-
 def test_loads_matlab_database_like_the_reference():
     """tests/golden/matlab_db.mat (oracle/make_golden_mat.py) -> the attributes the live reference's
     loader produced for the same file."""
