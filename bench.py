@@ -169,11 +169,14 @@ _TABLE = None       # (table, counts, hashbits, depth, maxtimebits, hashesperid)
 _QUERIES = None
 
 
-def _gen_query(args):
-    j, ntracks, first_seed, secs, qsecs, sigma = args
-    from audfprint_b200.synth import synth_track, synth_query
-    trk = j % ntracks
-    pcm, off = synth_query(synth_track(first_seed + trk, secs), j, seconds=qsecs, noise_sigma=sigma)
+_QTRACKS = None     # tracks the query workers cut excerpts from (set before their pool is forked)
+
+
+def _gen_query(j):
+    """Query j = a 10 s excerpt of track j % ntracks at a seeded offset + white noise (sigma 0.02 FS)."""
+    from audfprint_b200.synth import synth_query
+    trk = j % len(_QTRACKS)
+    pcm, off = synth_query(_QTRACKS[trk], j, seconds=10.0, noise_sigma=0.02)
     return pcm, trk, off
 
 
@@ -389,7 +392,7 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
     return out
 
 
-def bench_match_sharded(a, an, rows, roff, queries, rank, world):
+def bench_match_sharded(a, an, rows, roff, qpool, rank, world):
     """BASELINE configs[4]: the 2^20 x 100 table sharded by track-id range over the ranks; every
     rank probes its shard for ALL queries (K4 in publish mode), packs one record per query on the
     device, ONE NCCL all-gather of the record buffers, and merges on the device
@@ -406,7 +409,11 @@ def bench_match_sharded(a, an, rows, roff, queries, rank, world):
     ht.table, ht.counts, ht.hashesperid, ht.depth = table, counts, hpi, depth
     qan = Analyzer(device=an.device)
     qan.shifts = 4
-    qh = qan.fingerprint_batch([q[0] for q in queries])
+    qh = []
+    for b0 in range(0, a.match_queries, 10000):              # generate + fingerprint 10k queries at a time
+        part = qpool.map(_gen_query, range(b0, min(a.match_queries, b0 + 10000)), chunksize=32)
+        qh += qan.fingerprint_batch([q[0] for q in part])
+        del part
     nq = len(qh)
     B = max(1, min(a.match_batch, nq))
     batches = []
@@ -517,19 +524,28 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
     import torch.distributed as dist
     from audfprint_b200 import Analyzer, HashTable, _lib
     nsamp = int(round(a.seconds * SR))
-    tracks = make_tracks(pool, 10 ** 6 + rank * a.files, a.files, a.seconds)
-    pool.close()
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stride = (nsamp + 7) // 8 * 8
-    host_pcm = torch.zeros(a.files * stride + 8, dtype=torch.int16).pin_memory()
+    # the pool of distinct tracks goes to the device chunk by chunk (4 GB of int16 PCM per rank at
+    # 1024 x 180 s); only the first --e2e-files of them are also kept in pinned host memory
+    dev_pcm = torch.zeros(a.files * stride + 8, dtype=torch.int16, device="cuda")
+    ne2e = max(1, min(a.e2e_files, a.files))
+    host_pcm = torch.zeros(ne2e * stride + 8, dtype=torch.int16).pin_memory()
     hp = host_pcm.numpy()
-    for i, t in enumerate(tracks):
-        hp[i * stride:i * stride + nsamp] = t
+    for c0 in range(0, a.files, 128):
+        chunk = make_tracks(pool, 10 ** 6 + rank * a.files + c0, min(128, a.files - c0), a.seconds)
+        buf = np.zeros(len(chunk) * stride, np.int16)
+        for i, t in enumerate(chunk):
+            buf[i * stride:i * stride + nsamp] = t
+            if c0 + i < ne2e:
+                hp[(c0 + i) * stride:(c0 + i) * stride + nsamp] = t
+        dev_pcm[c0 * stride:(c0 + len(chunk)) * stride].copy_(torch.from_numpy(buf))
+    pool.close()
     offs = np.arange(a.files + 1, dtype=np.int64) * stride
     lens = np.full(a.files, nsamp, np.int64)
-    dev_pcm = host_pcm.cuda()
+    offs_e, lens_e = offs[:ne2e + 1], lens[:ne2e]
     an = Analyzer(device=local_rank)
     ctx = _lib.context(local_rank)
     stream = torch.cuda.current_stream()
@@ -543,9 +559,10 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(k, pcm):
-        an.fingerprint_packed(pcm, offs, fetch=False, sample_lengths=lens)
-        return ht.store_batch(["r%d/s%d/t%d" % (rank, k, i) for i in range(a.files)])
+    def step(k, pcm, o=None, ln=None):
+        o, ln = (offs, lens) if o is None else (o, ln)
+        an.fingerprint_packed(pcm, o, fetch=False, sample_lengths=ln)
+        return ht.store_batch(["r%d/s%d/t%d" % (rank, k, i) for i in range(len(ln))])
 
     # parity of the first batch against the host store() (pinned to the reference), rank 0
     parity = None
@@ -583,11 +600,12 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
     clocks = sampler.stop()
     ctx.set_profiling(False)
     ntracks = len(ht.names)
-    # end to end: pinned host PCM in every step
+    # end to end: pinned host PCM in every step (device calls of --e2e-files tracks)
+    step(999, hp, offs_e, lens_e)
     barrier()
     t0 = time.perf_counter()
     for k in range(a.steps):
-        step(1000 + k, hp)
+        step(1000 + k, hp, offs_e, lens_e)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
@@ -613,9 +631,10 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
                           "fanout": 3, "pks_per_frame": 5, "tracks_ingested_per_gpu": ntracks,
                           "cache": "inputs larger than L2", "parallelism": "file-sharded x%d, no collective" % world},
                "clocks": clocks,
-               "e2e": {"value": audio_s * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                       "h2d_bytes_per_step": int(hp.nbytes + offs.nbytes + lens.nbytes), "d2h_bytes_per_step": int(offs.nbytes),
-                       "ms_per_step": e2e_ms / a.steps},
+               "e2e": {"value": ne2e * a.seconds * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                       "files_per_device_call": ne2e,
+                       "h2d_bytes_per_step": int(hp.nbytes + offs_e.nbytes + lens_e.nbytes),
+                       "d2h_bytes_per_step": int(offs_e.nbytes), "ms_per_step": e2e_ms / a.steps},
                "gpu_launches": int(launches),
                "split_ms_per_step": {"fingerprint_kernels": fp_ms / a.steps, "store_and_host": ms_total / a.steps - fp_ms / a.steps},
                "roofline": {"kernel": "afp_stft_kernel<int16> (K1)", "bound": "hbm", "unit": "GB/s", "peak": peak,
@@ -654,6 +673,7 @@ def main():
                     help="queries of the match workload (0 = skip; default 10000 = BASELINE configs[2]; "
                          "100000 with --config 4)")
     ap.add_argument("--match-ids", type=int, default=1000000)
+    ap.add_argument("--e2e-files", type=int, default=256, help="--config 3: tracks per device call of the host-PCM leg")
     ap.add_argument("--match-batch", type=int, default=10000, help="queries per device call of the sharded match")
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
                     help="BASELINE.json configs[]: 1 batch fingerprint (default; the driver's line), 2 match 10k "
@@ -721,11 +741,16 @@ def main():
         return bench_ingest(a, rank, local_rank, world, cores, pool)
     tracks = make_tracks(pool, rank * a.files, a.files, a.seconds)
     do_match = a.match_queries > 0
-    queries = None
+    queries, qpool = None, None
     if do_match:
-        # queries are excerpts of RANK 0's tracks (a sharded table is the same table on every rank)
-        queries = pool.map(_gen_query, [(j, a.files, 0, a.seconds, 10.0, 0.02)
-                                        for j in range(a.match_queries)], chunksize=16)
+        # queries are excerpts of RANK 0's tracks (a sharded table is the same table on every rank);
+        # their pool is forked now (before CUDA is touched) with those tracks in memory, and asked for
+        # the queries batch by batch: 100k x 10 s of PCM never exist at once
+        global _QTRACKS
+        _QTRACKS = tracks if rank == 0 else make_tracks(pool, 0, a.files, a.seconds)
+        qpool = mp.get_context("fork").Pool(cores)
+        if world == 1:
+            queries = qpool.map(_gen_query, range(a.match_queries), chunksize=32)
     pool.close()
     want_cpu = rank == 0 and world == 1 and not a.no_cpu_baseline
     cpool = cpu_pool(tracks[:min(a.cpu_sample, a.files)], cores) if want_cpu else None
@@ -898,7 +923,7 @@ def main():
     if do_match and world == 1:
         match = bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream)
     elif do_match:
-        match = bench_match_sharded(a, an, rows, roff, queries, rank, world)
+        match = bench_match_sharded(a, an, rows, roff, qpool, rank, world)
 
     if rank == 0:
         peak, which = measured_peaks()
