@@ -65,6 +65,8 @@ _SIGS = {
     "afp_table_store_batch": (C.c_int, [_P, _P, C.c_int, _I64P, C.c_int32, _I64P, _I64P]),
     "afp_table_fetch_overflow": (C.c_int, [_P, _P, _P, _P]),
     "afp_table_apply_patches": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "afp_table_fetch_overflow_counts": (C.c_int, [_P, _P]),
+    "afp_table_apply_slots": (C.c_int, [_P, _P, C.c_int64]),
     "afp_table_download": (C.c_int, [_P, _P, _P]),
     "afp_mt_randint_replay": (C.c_int, [_P, _P, C.c_int64, _P]),
     "afp_table_restrict_ids": (C.c_int, [_P, C.c_int64, C.c_int64]),

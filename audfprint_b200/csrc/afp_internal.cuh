@@ -126,7 +126,7 @@ struct afp_ctx {
   int64_t nhits = -1, hits_nq = 0;
   // device-side HashTable.store (afp_store.cu)
   DevBuf d_st_off, d_st_ids, d_st_eval, d_st_seq, d_st_ovf, d_st_cnt, d_st_seg, d_st_heavy, d_st_part, d_st_scan;
-  DevBuf d_st_obkt, d_st_opos, d_st_oval;
+  DevBuf d_st_obkt, d_st_opos, d_st_oval, d_st_slot, d_st_last;
   int64_t store_novf = 0;
   DevBuf d_mfast, d_mqlist;    // fast path: member-hit lists; [count + pad][query list] handed to the general kernel
   int64_t match_general = 0;   // queries of the last batch the general kernel processed

@@ -170,6 +170,29 @@ __global__ void __launch_bounds__(SB) afp_ovf_compact_kernel(StoreArgs a, int64_
   }
 }
 
+// The host returns ONE int per overflow entry: the slot random.randint drew (>= depth: no write).
+// Several entries may name the same (bucket, slot); the sequential loop of the reference lets the
+// LAST one win.  `last` is a table-sized scratch of entry numbers (zero between calls):
+// pass A records the highest entry number per slot, pass B lets that entry write and clears.
+__global__ void afp_slots_mark_kernel(const uint32_t* bucket, const int32_t* slot, int64_t n, int depth, uint32_t* last) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  if (s >= 0 && s < depth) atomicMax(&last[(size_t)bucket[i] * depth + s], (uint32_t)(i + 1));
+}
+__global__ void afp_slots_write_kernel(const uint32_t* bucket, const int32_t* slot, const uint32_t* val, int64_t n,
+                                       int depth, uint32_t* last, uint32_t* table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  if (s < 0 || s >= depth) return;
+  const size_t k = (size_t)bucket[i] * depth + s;
+  if (last[k] == (uint32_t)(i + 1)) {
+    table[k] = val[i];
+    last[k] = 0u;                       // only the winner clears: the scratch is all-zero again
+  }
+}
+
 __global__ void afp_patch_kernel(uint32_t* table, int depth, const uint32_t* bucket, const int32_t* slot,
                                  const uint32_t* val, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,9 +332,12 @@ int afp_table_store_batch(afp_ctx* c, const int32_t* rows, int rows_on_host, con
   AFP_CUDA(c, cudaMemcpyAsync(&novf, part_off + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (novf > 0) {
-    AFP_CUDA(c, c->d_st_obkt.reserve(sizeof(uint32_t) * (size_t)novf));
-    AFP_CUDA(c, c->d_st_opos.reserve(sizeof(int32_t) * (size_t)novf));
-    AFP_CUDA(c, c->d_st_oval.reserve(sizeof(uint32_t) * (size_t)novf));
+    // sized for the whole batch at once: the overflow grows from step to step as the table fills, and
+    // every regrowth would be a cudaFree + cudaMalloc in the middle of an ingest
+    AFP_CUDA(c, c->d_st_obkt.reserve(sizeof(uint32_t) * (size_t)M));
+    AFP_CUDA(c, c->d_st_opos.reserve(sizeof(int32_t) * (size_t)M));
+    AFP_CUDA(c, c->d_st_oval.reserve(sizeof(uint32_t) * (size_t)M));
+    AFP_CUDA(c, c->d_st_slot.reserve(sizeof(int32_t) * (size_t)M));
     afp_ovf_compact_kernel<<<(unsigned)nblk, SB, 0, c->stream>>>(a, M, part_off, c->d_st_obkt.as<uint32_t>(),
                                                                 c->d_st_opos.as<int32_t>(), c->d_st_oval.as<uint32_t>());
     AFP_CUDA(c, cudaGetLastError());
@@ -334,6 +360,46 @@ int afp_table_fetch_overflow(afp_ctx* c, uint32_t* bucket, int32_t* count_before
     AFP_CUDA(c, cudaMemcpyAsync(value, c->d_st_oval.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
   }
   AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return AFP_OK;
+}
+
+int afp_table_fetch_overflow_counts(afp_ctx* c, int32_t* count_before) {
+  if (!c) return AFP_ERR_INVALID;
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->store_novf;
+  if (n) {
+    if (!count_before) return AFP_ERR_INVALID;
+    AFP_CUDA(c, cudaMemcpyAsync(count_before, c->d_st_opos.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return AFP_OK;
+}
+
+int afp_table_apply_slots(afp_ctx* c, const int32_t* slot, int64_t n) {
+  if (!c || n < 0 || (n > 0 && !slot)) return AFP_ERR_INVALID;
+  if (!c->tab.loaded) AFP_FAIL(c, AFP_ERR_STATE, "no table on the device");
+  if (n != c->store_novf) AFP_FAIL(c, AFP_ERR_INVALID, "one slot per overflow entry of the last afp_table_store_batch");
+  AFP_CUDA(c, cudaSetDevice(c->device));
+  if (n == 0) return AFP_OK;
+  if (n >= ((int64_t)1 << 32) - 1) AFP_FAIL(c, AFP_ERR_UNSUPPORTED, "too many overflow entries");
+  const size_t cells = ((size_t)1 << c->tab.hashbits) * (size_t)c->tab.depth;
+  if (c->d_st_last.cap < cells * sizeof(uint32_t)) {
+    AFP_CUDA(c, c->d_st_last.reserve(cells * sizeof(uint32_t)));
+    AFP_CUDA(c, cudaMemsetAsync(c->d_st_last.p, 0, cells * sizeof(uint32_t), c->stream));
+  }
+  AFP_CUDA(c, c->d_st_slot.reserve(sizeof(int32_t) * (size_t)n));
+  AFP_CUDA(c, cudaMemcpyAsync(c->d_st_slot.p, slot, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  afp_slots_mark_kernel<<<grid, 256, 0, c->stream>>>(c->d_st_obkt.as<uint32_t>(), c->d_st_slot.as<int32_t>(), n,
+                                                     c->tab.depth, c->d_st_last.as<uint32_t>());
+  AFP_CUDA(c, cudaGetLastError());
+  afp_slots_write_kernel<<<grid, 256, 0, c->stream>>>(c->d_st_obkt.as<uint32_t>(), c->d_st_slot.as<int32_t>(),
+                                                      c->d_st_oval.as<uint32_t>(), n, c->tab.depth,
+                                                      c->d_st_last.as<uint32_t>(), c->tab.table.as<uint32_t>());
+  AFP_CUDA(c, cudaGetLastError());
+  c->launches += 2;
+  AFP_CUDA(c, cudaStreamSynchronize(c->stream));     // `slot` is the caller's
+  c->store_novf = 0;
   return AFP_OK;
 }
 

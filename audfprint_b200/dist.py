@@ -262,7 +262,8 @@ def match_sharded_batch(matcher, ht, packed_queries, row_cap: int = 16, group=No
     import torch
     from . import _lib
     qrows, qoff = packed_queries
-    qrows = np.ascontiguousarray(qrows, dtype=np.int32).reshape(-1, 2)
+    if not hasattr(qrows, "data_ptr"):            # a torch CUDA tensor (int32 [R][2]) is used in place
+        qrows = np.ascontiguousarray(qrows, dtype=np.int32).reshape(-1, 2)
     qoff = np.ascontiguousarray(qoff, dtype=np.int64)
     nq = len(qoff) - 1
     sd = max(int(matcher.search_depth), 1)

@@ -20,6 +20,7 @@ import math
 import os
 import pickle
 import random
+import sys
 import weakref
 
 import numpy as np
@@ -231,8 +232,15 @@ class HashTable(object):
             return []
         if self._shard is not None:
             raise AfpStateError("the device copy is a shard (restrict_device_ids): cannot store into it")
+        import time as _time
+        prof = os.environ.get("AFP_STORE_PROFILE")
+        tp = [_time.perf_counter()]
         ctx = self._sync_device()                 # the device holds this table's current state
+        if prof:
+            ctx.sync()
+        tp.append(_time.perf_counter())
         ids = self._names_to_ids(names)           # (host bookkeeping; the device copy stays the current one)
+        tp.append(_time.perf_counter())
         nov = C.c_int64(0)
         if hashes is None:
             roff = np.empty(nfiles + 1, np.int64)
@@ -247,30 +255,34 @@ class HashTable(object):
             ctx.check(ctx.lib.afp_table_store_batch(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                     roff.ctypes.data_as(C.POINTER(C.c_int64)), nfiles,
                                                     ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nov)))
+        tp.append(_time.perf_counter())
         n = int(nov.value)
         if n:
-            bucket, cnt, val = np.empty(n, np.uint32), np.empty(n, np.int32), np.empty(n, np.uint32)
-            ctx.check(ctx.lib.afp_table_fetch_overflow(ctx.h, bucket.ctypes.data, cnt.ctypes.data, val.ctypes.data))
+            # overflow entries: only their counts come to the host; random.randint(0, count) is
+            # replayed for each, in sequence, on a C copy of CPython's generator; the drawn slots go
+            # back and the device applies them (the last entry of a slot wins, as in the reference)
+            cnt = np.empty(n, np.int32)
+            ctx.check(ctx.lib.afp_table_fetch_overflow_counts(ctx.h, cnt.ctypes.data))
             st = random.getstate()
             state = np.array(st[1], dtype=np.uint32)
             slot = np.empty(n, np.int32)
+            tp.append(_time.perf_counter())
             ctx.check(ctx.lib.afp_mt_randint_replay(state.ctypes.data, cnt.ctypes.data, n, slot.ctypes.data))
-            random.setstate((st[0], tuple(int(x) for x in state), st[2]))
-            hit = np.nonzero((slot >= 0) & (slot < self.depth))[0]
-            if len(hit):
-                # several draws may name one slot: the last one in sequence wins (np.unique keeps the
-                # first occurrence, so look at the sequence backwards)
-                key = bucket[hit].astype(np.int64) * self.depth + slot[hit]
-                _, first_rev = np.unique(key[::-1], return_index=True)
-                keep = hit[len(hit) - 1 - first_rev]
-                b, sl, v = (np.ascontiguousarray(x[keep]) for x in (bucket, slot, val))
-                ctx.check(ctx.lib.afp_table_apply_patches(ctx.h, b.ctypes.data, sl.ctypes.data, v.ctypes.data, len(keep)))
+            random.setstate((st[0], tuple(state.tolist()), st[2]))
+            tp.append(_time.perf_counter())
+            ctx.check(ctx.lib.afp_table_apply_slots(ctx.h, slot.ctypes.data, n))
+            tp.append(_time.perf_counter())
         per_track = np.diff(roff)
         np.add.at(self.__dict__["_hashesperid"], ids, per_track.astype(np.uint32))
         hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
         ctx.check(ctx.lib.afp_table_set_hashesperid(ctx.h, hpi.ctypes.data if len(hpi) else None, len(hpi)))
         self._touch()
         self._dev_newer = True
+        if prof:
+            tp.append(_time.perf_counter())
+            print("store_batch: files %d overflow %d | " % (nfiles, n) +
+                  " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(tp[:-1], tp[1:])) + " ms "
+                  "(sync, names, device store, [fetch counts, replay, apply,] hpi)", file=sys.stderr)
         ctx.table_key = self._dev_key = self._stamp()      # the device copy IS this version
         ctx.table_owner = weakref.ref(self)
         return [int(x) for x in per_track]

@@ -48,10 +48,11 @@ class Matcher(object):
         """afp_match_batch, growing the per-query row capacity when a query overflows it."""
         total = C.c_int64(0)
         cap = 256
+        ptr, on_host = _lib.ptr_of(packed) if len(packed) else (None, 1)     # NumPy (host) or torch CUDA tensor
         while True:
             p.row_capacity = cap
             try:
-                ctx.check(ctx.lib.afp_match_batch(ctx.h, packed.ctypes.data if len(packed) else None, 1, nq,
+                ctx.check(ctx.lib.afp_match_batch(ctx.h, ptr, on_host, nq,
                                                   qoff.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(p),
                                                   C.byref(total)))
                 return int(total.value)

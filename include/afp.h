@@ -213,6 +213,12 @@ int afp_table_store_batch(afp_ctx* ctx, const int32_t* rows, int rows_on_host, c
 int afp_table_fetch_overflow(afp_ctx* ctx, uint32_t* bucket, int32_t* count_before, uint32_t* value);
 int afp_table_apply_patches(afp_ctx* ctx, const uint32_t* bucket, const int32_t* slot, const uint32_t* value,
                             int64_t n);
+/* The same exchange with less traffic (what HashTable.store_batch uses): only the counts travel to
+ * the host (the RNG replay needs nothing else), one drawn slot per overflow entry comes back (HOST
+ * int32 [noverflow], sequence order; a slot >= depth writes nothing), and the device applies them
+ * itself, the LAST entry of a slot winning as in the reference's sequential loop. */
+int afp_table_fetch_overflow_counts(afp_ctx* ctx, int32_t* count_before);
+int afp_table_apply_slots(afp_ctx* ctx, const int32_t* slot, int64_t n);
 /* Copy the device table back: table uint32 [2^hashbits][depth], counts int32 [2^hashbits] (HOST). */
 int afp_table_download(afp_ctx* ctx, uint32_t* table, int32_t* counts);
 /* CPython's `random.randint(0, count)` replayed for n draws.  state625 = the 625 uint32 of
