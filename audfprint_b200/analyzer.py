@@ -263,17 +263,21 @@ class Analyzer(object):
                 self._account(len(sig) / self.target_sr)
             return [len(h) for h in hashes]
         nsh = max(1, int(self.shifts))
-        counts, start, acc = [], 0, 0
+        counts, start, acc, pending = [], 0, 0, None
         frames = [nsh * (1 + len(x) // self.n_hop) for x in signals]
         for i in range(len(signals) + 1):
             if i == len(signals) or (acc + frames[i] > self.max_frames_per_call and i > start):
                 if i > start:
                     packed, starts, lens = self._pack(signals[start:i])
                     self.fingerprint_packed(packed, starts, nsh, fetch=False, sample_lengths=lens)
-                    counts += hashtable.store_batch(names[start:i])
+                    # the host-side RNG replay of the previous call's overflow runs while the GPU
+                    # fingerprints this one
+                    counts += hashtable.store_batch_finish(pending)
+                    pending = hashtable.store_batch_begin(names[start:i])
                 start, acc = i, 0
             if i < len(signals):
                 acc += frames[i]
+        counts += hashtable.store_batch_finish(pending)
         for sig in signals:
             self._account(len(sig) / self.target_sr)
         return counts

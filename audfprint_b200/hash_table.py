@@ -148,7 +148,7 @@ class HashTable(object):
         if getattr(self, "_dev_newer", False):
             self._pull_device()
         st = dict(self.__dict__)
-        for k in ("_token", "_version", "_dev_newer", "_shard", "_dev_key"):
+        for k in ("_token", "_version", "_dev_newer", "_shard", "_dev_key", "_store_pending"):
             st.pop(k, None)
         for k in ("table", "counts", "hashesperid"):      # the reference's attribute names
             st[k] = st.pop("_" + k)
@@ -227,20 +227,25 @@ class HashTable(object):
         (and `random`'s state advanced accordingly), and the winning writes return as patches.
         Afterwards the DEVICE copy is the current one; `table` / `counts` refresh themselves from
         it when read.  Returns the number of hashes stored per track."""
+        return self.store_batch_finish(self.store_batch_begin(names, hashes))
+
+    def store_batch_begin(self, names, hashes=None):
+        """First half of store_batch: everything up to and including the device kernels (slots
+        below `depth` written, overflow entries compacted, their counts fetched).  The returned
+        token goes to store_batch_finish, which replays `random.randint` for the overflow on the
+        host and applies the result.  Analyzer.ingest_batch launches the NEXT batch's fingerprint
+        kernels between the two, so the (sequential, host-side) RNG replay of batch k runs while the
+        GPU fingerprints batch k+1; finishes must be called in the order of the begins, each
+        before the next begin."""
         nfiles = len(names)
         if nfiles == 0:
-            return []
+            return None
         if self._shard is not None:
             raise AfpStateError("the device copy is a shard (restrict_device_ids): cannot store into it")
-        import time as _time
-        prof = os.environ.get("AFP_STORE_PROFILE")
-        tp = [_time.perf_counter()]
+        if getattr(self, "_store_pending", False):
+            raise AfpStateError("store_batch_begin: the previous batch was not finished")
         ctx = self._sync_device()                 # the device holds this table's current state
-        if prof:
-            ctx.sync()
-        tp.append(_time.perf_counter())
         ids = self._names_to_ids(names)           # (host bookkeeping; the device copy stays the current one)
-        tp.append(_time.perf_counter())
         nov = C.c_int64(0)
         if hashes is None:
             roff = np.empty(nfiles + 1, np.int64)
@@ -255,36 +260,41 @@ class HashTable(object):
             ctx.check(ctx.lib.afp_table_store_batch(ctx.h, rows.ctypes.data if len(rows) else None, 1,
                                                     roff.ctypes.data_as(C.POINTER(C.c_int64)), nfiles,
                                                     ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nov)))
-        tp.append(_time.perf_counter())
         n = int(nov.value)
+        cnt = np.empty(n, np.int32)
         if n:
-            # overflow entries: only their counts come to the host; random.randint(0, count) is
-            # replayed for each, in sequence, on a C copy of CPython's generator; the drawn slots go
-            # back and the device applies them (the last entry of a slot wins, as in the reference)
-            cnt = np.empty(n, np.int32)
             ctx.check(ctx.lib.afp_table_fetch_overflow_counts(ctx.h, cnt.ctypes.data))
+        # from here on the device table is ahead of the host arrays, whatever happens next
+        self._touch()
+        self._dev_newer = True
+        ctx.table_key = self._dev_key = self._stamp()
+        ctx.table_owner = weakref.ref(self)
+        self._store_pending = True
+        return (ctx, ids, roff, cnt)
+
+    def store_batch_finish(self, token):
+        """Second half of store_batch (see store_batch_begin).  Returns the hashes per track."""
+        if token is None:
+            return []
+        ctx, ids, roff, cnt = token
+        n = len(cnt)
+        if n:
+            # overflow entries: random.randint(0, count) is replayed for each, in sequence, on a C
+            # copy of CPython's generator; the drawn slots go back and the device applies them (the
+            # last entry of a slot wins, as in the reference's sequential loop)
             st = random.getstate()
             state = np.array(st[1], dtype=np.uint32)
             slot = np.empty(n, np.int32)
-            tp.append(_time.perf_counter())
             ctx.check(ctx.lib.afp_mt_randint_replay(state.ctypes.data, cnt.ctypes.data, n, slot.ctypes.data))
             random.setstate((st[0], tuple(state.tolist()), st[2]))
-            tp.append(_time.perf_counter())
             ctx.check(ctx.lib.afp_table_apply_slots(ctx.h, slot.ctypes.data, n))
-            tp.append(_time.perf_counter())
         per_track = np.diff(roff)
         np.add.at(self.__dict__["_hashesperid"], ids, per_track.astype(np.uint32))
         hpi = np.ascontiguousarray(self.hashesperid, dtype=np.uint32)
         ctx.check(ctx.lib.afp_table_set_hashesperid(ctx.h, hpi.ctypes.data if len(hpi) else None, len(hpi)))
+        self._store_pending = False
         self._touch()
-        self._dev_newer = True
-        if prof:
-            tp.append(_time.perf_counter())
-            print("store_batch: files %d overflow %d | " % (nfiles, n) +
-                  " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(tp[:-1], tp[1:])) + " ms "
-                  "(sync, names, device store, [fetch counts, replay, apply,] hpi)", file=sys.stderr)
         ctx.table_key = self._dev_key = self._stamp()      # the device copy IS this version
-        ctx.table_owner = weakref.ref(self)
         return [int(x) for x in per_track]
 
     def _names_to_ids(self, names):

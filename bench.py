@@ -590,11 +590,17 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fp_ms, k1_ms = 0.0, 0.0
     e0.record(stream)
+    pending = None
     for k in range(a.steps):
-        step(k, dev_pcm)
+        # as Analyzer.ingest_batch does: batch k's fingerprint kernels are launched, THEN the store of
+        # batch k-1 is finished (host-side RNG replay of its overflow), THEN batch k is stored
+        an.fingerprint_packed(dev_pcm, offs, fetch=False, sample_lengths=lens)
+        ht.store_batch_finish(pending)
+        pending = ht.store_batch_begin(["r%d/s%d/t%d" % (rank, k, i) for i in range(a.files)])
         st_ms = ctx.stage_ms()
         fp_ms += sum(st_ms[1:])
         k1_ms += st_ms[1]
+    ht.store_batch_finish(pending)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -606,8 +612,12 @@ def bench_ingest(a, rank, local_rank, world, cores, pool):
     step(999, hp, offs_e, lens_e)
     barrier()
     t0 = time.perf_counter()
+    pending = None
     for k in range(a.steps):
-        step(1000 + k, hp, offs_e, lens_e)
+        an.fingerprint_packed(hp, offs_e, fetch=False, sample_lengths=lens_e)
+        ht.store_batch_finish(pending)
+        pending = ht.store_batch_begin(["r%d/s%d/t%d" % (rank, 1000 + k, i) for i in range(ne2e)])
+    ht.store_batch_finish(pending)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
