@@ -962,6 +962,8 @@ def main():
                "roofline": {"kernel": "afp_stft_kernel<int16> (K1: frame+window+512-pt real FFT+log|.|, FP64)",
                             "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which,
                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "traffic_source": "dram__bytes_read+write of one launch, ncu --set full capture "
+                                              "profiles/r01_v5_k1_stft.txt (K1 is unchanged since)",
                             "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": k1_ms},
                "stages_ms": {"h2d": float(stages[0]), "k1_stft_log": float(stages[1]),
                              "stats": float(stages[2]), "k2_peaks": float(stages[3]),
