@@ -269,6 +269,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
+def warm_up(fn, min_seconds=0.7, min_calls=3):
+    """Run `fn` until the GPU has been busy for min_seconds: the match legs follow CPU-only phases
+    (generators, CPU baseline) during which the SM clock falls to idle (120 MHz), and a couple of
+    20 ms calls are not enough to bring it back - a run of this bench measured the same kernels
+    2.4x slower that way."""
+    import torch
+    t0 = time.perf_counter()
+    n = 0
+    while n < min_calls or time.perf_counter() - t0 < min_seconds:
+        fn()
+        n += 1
+    torch.cuda.synchronize()
+
+
 def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream):
     """BASELINE configs[2]: 10 s noisy excerpts (4 shifts) against a 1M-id device-resident
     table (2^20 buckets x 100, every bucket full).  Reports match-only queries/s with the
@@ -297,8 +311,8 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
     fp_s = time.perf_counter() - t0
     m = Matcher()
     m.window = 2                      # CLI default --match-win 2 (audfprint.py:363)
-    for _ in range(2):
-        res = m.match_batch(ht, (qrows, qoff))
+    res = m.match_batch(ht, (qrows, qoff))
+    warm_up(lambda: m.match_batch(ht, (qrows, qoff)))
     # --- match only, host hashes in / rows out (includes H2D of the query hashes, D2H of rows)
     steps = 5
     torch.cuda.synchronize()
@@ -316,15 +330,16 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
 
     def dev_step():
         ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(p), C.byref(tot)))
-    for _ in range(2):
-        dev_step()
-    torch.cuda.synchronize()
+    warm_up(dev_step)
+    msampler = ClockSampler(an.device if an.device is not None else 0)
+    msampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         dev_step()
     e1.record(stream)
     torch.cuda.synchronize()
+    mclocks = msampler.stop()
     dev_s = e0.elapsed_time(e1) * 1e-3 / steps
     st = Matcher.last_status(ht, nq)
     fast_stats = {"queries_on_fast_kernel": int(np.sum(st[:, 0] == 0)),
@@ -338,6 +353,8 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
     pg.force_general = 1
     ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(pg), C.byref(tot)))
     torch.cuda.synchronize()
+    warm_up(lambda: ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, nq, qoffp, C.byref(pg), C.byref(tot))),
+            min_seconds=0.3, min_calls=1)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(stream)
     for _ in range(2):
@@ -358,7 +375,7 @@ def bench_match(a, an, ctx, tracks, rows, roff, queries, cores, want_cpu, stream
     nprobe = 12 * nqh + 4 * nqh * depth + 28 * sum(len(r) for r in res)      # SURVEY.md §8d B_m
     out = {"metric": "match_queries_per_sec", "queries": nq, "table": "2^%d buckets x %d, %d ids, every bucket "
            "full (SURVEY.md 8d config 3)" % (hashbits, depth, a.match_ids), "query_hashes": nqh,
-           "value": nq / dev_s, "unit": "queries/s", "ms_per_step": dev_s * 1e3,
+           "value": nq / dev_s, "unit": "queries/s", "ms_per_step": dev_s * 1e3, "clocks": mclocks,
            "e2e": {"value": nq / host_s, "unit": "queries/s", "h2d_bytes_per_step": int(qrows.nbytes + qoff.nbytes),
                    "d2h_bytes_per_step": int(sum(r.nbytes for r in res) + qoff.nbytes)},
            "audio_to_result": {"value": nq / audio_s, "unit": "queries/s",
@@ -443,8 +460,7 @@ def bench_match_sharded(a, an, rows, roff, qpool, rank, world):
     pp = m._params()
     tot = C.c_int64(0)
     offp = np.ascontiguousarray(my_off).ctypes.data_as(C.POINTER(C.c_int64))
-    for _ in range(2):
-        ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, len(mine), offp, C.byref(pp), C.byref(tot)))
+    warm_up(lambda: ctx.check(ctx.lib.afp_match_batch(ctx.h, dq.data_ptr(), 0, len(mine), offp, C.byref(pp), C.byref(tot))))
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -461,9 +477,8 @@ def bench_match_sharded(a, an, rows, roff, qpool, rank, world):
     ht.restrict_device_ids(lo, hi)
     res = None
     dbatches = [(torch.from_numpy(qb[0]).cuda(), qb[1]) for qb in batches]   # query hashes resident, like the N=1 `value`
-    for _ in range(2):
-        for qb in dbatches[:2]:
-            afd.match_sharded_batch(m, ht, qb, row_cap=16, fetch=False)
+    for k in range(24):         # collective calls: the same count on every rank; ~0.4 s of GPU work
+        afd.match_sharded_batch(m, ht, dbatches[k % len(dbatches)], row_cap=16, fetch=False)
     steps = 3
     dist.barrier()
     torch.cuda.synchronize()
