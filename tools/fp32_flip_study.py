@@ -4,7 +4,8 @@ hashes relative to the FP64 (reference-identical) path?  VERDICT r1 #6(b) asked 
 5 lengths, plus the adversarial inputs of tests/cases.py.  Writes profiles/r02_fp32_flip_study.json."""
 import json, sys, time, multiprocessing as mp
 import numpy as np
-sys.path.insert(0, '/root/repo')
+ROOT = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from audfprint_b200.synth import synth_track
 from tests import cases
 
@@ -44,7 +45,7 @@ def main(total=100_000, chunk=4096):
            "hash_flip_rate": nsym / max(1, nhash), "worst_files": sorted(worst, reverse=True)[:10],
            "adversarial": adv, "wall_s": time.time() - t0,
            "note": "FP32 STFT + MUFU log + float spectrogram (K1), K2 thresholds in FP64 either way"}
-    json.dump(out, open('/root/repo/gpurun_out/r02_fp32_flip_study.json', 'w'), indent=1)
+    json.dump(out, open(ROOT + '/gpurun_out/r02_fp32_flip_study.json', 'w'), indent=1)
     print(json.dumps({k: out[k] for k in ("files", "files_with_any_difference", "file_flip_rate", "hash_flip_rate", "wall_s")}))
     print(adv)
 

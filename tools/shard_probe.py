@@ -2,7 +2,8 @@
 publish mode + device pack + device merge of that one shard, timed; run under ncu for the profile."""
 import sys, time, ctypes as C
 import numpy as np
-sys.path.insert(0, '/root/repo')
+ROOT = __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import bench
 import multiprocessing as mp
 nfiles, nq = 512, 4096
