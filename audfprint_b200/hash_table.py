@@ -5,10 +5,12 @@ The public attributes the reference's callers read directly (`table`, `counts`,
 `names`, `hashesperid`, `params`, `hashbits`, `depth`, `maxtimebits`, `dirty`,
 `ht_version`) are plain host NumPy arrays / Python objects and remain the
 source of truth; `get_hits` (the hot method, 92 % of the reference's match
-time) runs on the GPU against a lazily refreshed device copy.  Mutation
-(`store`, `merge`, `remove`) is host bookkeeping — the "next" row §8f-1 of
-SURVEY.md — written so that it reproduces the reference's results exactly,
-including its draws from the global `random` module on bucket overflow.
+time) runs on the GPU against a lazily refreshed device copy.  `store` exists
+twice: per track on the host, and batched on the device (`store_batch`,
+SURVEY.md §8f-1: the device copy then leads and the host arrays refresh from it
+when read); `merge` and `remove` are host bookkeeping.  All of them reproduce the
+reference's results exactly, including its draws from the global `random` /
+`np.random` generators on bucket overflow.
 """
 from __future__ import annotations
 
