@@ -126,3 +126,48 @@ def test_ingest_batch_on_device_equals_per_file_store_and_serves_matches():
     _ = m.match_batch(dev, qs)                                       # re-upload after `host` took the device: still right
     assert np.array_equal(dev.table, host.table) and np.array_equal(dev.counts, host.counts)
     assert np.array_equal(dev.hashesperid, host.hashesperid) and dev.names == host.names
+
+
+def test_overflow_exchange_through_the_patch_form_of_the_abi(golden_match):
+    """The other form of the overflow exchange in include/afp.h - afp_table_fetch_overflow
+    (bucket, count, value) + afp_table_apply_patches with ONE patch per slot chosen by the caller -
+    builds the same table as store_batch (which sends only the drawn slots back)."""
+    import ctypes as C
+    gm = golden_match
+    tracks = [gm["track%d/hashes" % i] for i in range(12)]
+    hashbits, depth, mtb = 10, 6, 12
+    random.seed(77)
+    ref = HashTable(hashbits=hashbits, depth=depth, maxtime=1 << mtb)
+    ref.store_batch(["t%d" % i for i in range(12)], tracks)
+    want_table, want_counts = ref.table.copy(), ref.counts.copy()
+    after = random.random()
+
+    random.seed(77)
+    ctx = _lib.context(None)
+    ctx.table_key = None                                   # the context's table is ours now
+    ctx.check(ctx.lib.afp_table_create(ctx.h, hashbits, depth, mtb))
+    roff = np.zeros(13, np.int64)
+    roff[1:] = np.cumsum([len(t) for t in tracks])
+    rows = np.ascontiguousarray(np.concatenate(tracks), dtype=np.int32)
+    ids = np.arange(12, dtype=np.int64)
+    nov = C.c_int64(0)
+    ctx.check(ctx.lib.afp_table_store_batch(ctx.h, rows.ctypes.data, 1, roff.ctypes.data_as(C.POINTER(C.c_int64)), 12,
+                                            ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nov)))
+    n = int(nov.value)
+    assert n > 1000                                        # 2^10 x 6: most rows overflow
+    bucket, cnt, val = np.empty(n, np.uint32), np.empty(n, np.int32), np.empty(n, np.uint32)
+    ctx.check(ctx.lib.afp_table_fetch_overflow(ctx.h, bucket.ctypes.data, cnt.ctypes.data, val.ctypes.data))
+    slot = np.array([random.randint(0, int(c)) for c in cnt])          # the reference's own draws
+    hit = np.nonzero(slot < depth)[0]
+    last = {}
+    for i in hit:                                          # sequential semantics: the last write of a slot wins
+        last[(int(bucket[i]), int(slot[i]))] = int(val[i])
+    pb = np.array([k[0] for k in last], np.uint32)
+    ps = np.array([k[1] for k in last], np.int32)
+    pv = np.array(list(last.values()), np.uint32)
+    ctx.check(ctx.lib.afp_table_apply_patches(ctx.h, pb.ctypes.data, ps.ctypes.data, pv.ctypes.data, len(pb)))
+    table = np.empty((1 << hashbits, depth), np.uint32)
+    counts = np.empty(1 << hashbits, np.int32)
+    ctx.check(ctx.lib.afp_table_download(ctx.h, table.ctypes.data, counts.ctypes.data))
+    assert random.random() == after
+    assert np.array_equal(counts, want_counts) and np.array_equal(table, want_table)
