@@ -100,7 +100,18 @@ class Matcher(object):
         nq = len(qoff) - 1
         p = self._params()
         if self.exact_count or self.find_time_range:
-            out = [self._match_with_options(ht, packed[qoff[i]:qoff[i + 1]]) for i in range(nq)]
+            # TWO device calls for the whole batch - the hits of every query row (afp_get_hits) and
+            # the ranked candidate lists + approximate rows (afp_match_batch, publish mode) - then the
+            # reference's per-candidate post-processing on the host, query by query
+            hits = ht.get_hits(packed)
+            mask = (1 << int(ht.hashbits)) - 1
+            per_row = np.minimum(int(ht.depth), ht.counts[packed[:, 1].astype(np.int64) & mask]).astype(np.int64)
+            hoff = np.concatenate([[0], np.cumsum(per_row)])[qoff]
+            rows, roff, cand, cnts = self._publish_call(ht, packed, qoff)
+            out = []
+            for i in range(nq):
+                pre = (hits[hoff[i]:hoff[i + 1]], rows[roff[i]:roff[i + 1]], cand[i], cnts[i])
+                out.append(self._match_with_options(ht, packed[qoff[i]:qoff[i + 1]], device_results=pre))
             return [r[(-r[:, 1]).argsort(), ] for r in out] if sort else out
         ctx = ht._sync_device()
         rows = np.empty((self._run(ctx, p, packed, nq, qoff), 7), np.int32)
@@ -163,12 +174,20 @@ class Matcher(object):
         cut = np.nonzero(np.diff(h[:, 0]))[0] + 1
         return {int(part[0, 0]): part for part in np.split(h, cut)}
 
-    def _match_with_options(self, ht, q, hashesfor=None):
+    def _match_with_options(self, ht, q, hashesfor=None, device_results=None):
         """Rows of match_hashes for exact_count / find_time_range (unsorted: candidate-rank
-        order), plus the matching (time, hash) pairs of row `hashesfor` of the SORTED result."""
+        order), plus the matching (time, hash) pairs of row `hashesfor` of the SORTED result.
+        device_results = (hits, rows, cand, counts) of this query when match_batch already fetched
+        them for the whole batch."""
         q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 2)
-        hits = ht.get_hits(q)
-        approx, ids, raws = self._device_rows_and_candidates(ht, q)
+        if device_results is None:
+            hits = ht.get_hits(q)
+            approx, ids, raws = self._device_rows_and_candidates(ht, q)
+        else:
+            hits, rows_q, cand_q, cnt_q = device_results
+            depth = max(0, min(int(cnt_q[1]), int(self.search_depth), int(cnt_q[0])))
+            approx = rows_q[rows_q[:, 4] < depth]
+            ids, raws = cand_q[:depth, 0].astype(np.int64), cand_q[:depth, 1].astype(np.int64)
         by_id = self._split_by_id(hits)
         if not self.exact_count:
             rows = approx.copy()

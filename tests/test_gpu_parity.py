@@ -188,6 +188,12 @@ def test_matcher_options_vs_reference_golden(golden_match, golden_options, db):
                     rows = m.match_hashes(ht, q)
                     assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1])
                 assert sorted(map(tuple, rows)) == sorted(map(tuple, orows)), (db, key, cfg)
+        # the batch form fetches hits and candidates of ALL queries with two device calls
+        qs = [gm["q%d_%s/q" % (j, tag)] for j in range(cases.DB_QUERIES) for tag in ("clean", "noisy")]
+        qs.insert(3, np.zeros((0, 2), np.int32))
+        for got, q in zip(m.match_batch(ht, qs, sort=False), qs):
+            one = m._match_with_options(ht, q) if len(q) else np.zeros((0, 7), np.int32)
+            assert np.array_equal(got, one), (db, cfg)
     assert nexact > 40
 
 
