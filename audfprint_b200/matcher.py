@@ -103,8 +103,11 @@ class Matcher(object):
             # TWO device calls for the whole batch - the hits of every query row (afp_get_hits) and
             # the ranked candidate lists + approximate rows (afp_match_batch, publish mode) - then the
             # reference's per-candidate post-processing on the host, query by query
+            if nq == 1:                          # match_hashes: the per-query form of the same two calls
+                r = self._match_with_options(ht, packed)
+                return [r[(-r[:, 1]).argsort(), ] if sort else r]
             hits = ht.get_hits(packed)
-            mask = (1 << int(ht.hashbits)) - 1
+            mask =(1 << int(ht.hashbits)) - 1
             per_row = np.minimum(int(ht.depth), ht.counts[packed[:, 1].astype(np.int64) & mask]).astype(np.int64)
             hoff = np.concatenate([[0], np.cumsum(per_row)])[qoff]
             rows, roff, cand, cnts = self._publish_call(ht, packed, qoff)
