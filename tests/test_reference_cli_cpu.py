@@ -129,3 +129,34 @@ def test_reference_cli_runs_on_the_mirror_classes(tmp_path, golden_match):
     # and the reference itself loads what the mirror wrote
     out = _run(str(tmp_path), False, [["list", "--dbase", dbs["mirror"][2]]])
     assert "trk00.afpt" in out and "trk09.afpt" in out
+
+
+def test_reference_multiprocess_add_on_the_mirror_classes(tmp_path, golden_match):
+    """`new --ncores 2` (audfprint.py:199-235): the reference forks one process per file list,
+    each builds a table of the swapped-in class, pickles it back through a pipe and the parent
+    merges them - the mirror objects have to survive that round trip (threading /
+    processes) and give the table the pure reference gives.  Geometry: 37 slots hold every bucket
+    of either child (CPython reseeds `random` in a forked child, so overflow draws THERE differ
+    from run to run in the reference itself), while four buckets of the merged table overflow and
+    take the parent's seeded np.random.permutation draws (hash_table.py:309-313)."""
+    gm = golden_match
+    from audfprint_b200.analyzer import hashes_save
+    names = []
+    for i in range(10):
+        fn = str(tmp_path / ("mp%02d.afpt" % i))
+        hashes_save(fn, gm["track%d/hashes" % i])
+        names.append(fn)
+    geo = ["--hashbits", "10", "--bucketsize", "37", "--maxtimebits", "12"]
+    out = {}
+    for tag, swap in (("mirror", True), ("ref", False)):
+        db = str(tmp_path / (tag + "_mp.pklz"))
+        text = _run(str(tmp_path), swap, [["new", "--dbase", db, "--ncores", "2"] + geo + names])
+        out[tag] = (_load_db(db), text)
+    m, r = out["mirror"][0], out["ref"][0]
+    assert m.names == r.names and len(m.names) == 10
+    assert m.names[:5] == names[0::2] and m.names[5:] == names[1::2]        # the ix % ncores deal, core by core
+    assert np.array_equal(m.counts, r.counts) and np.array_equal(m.table, r.table)
+    assert np.array_equal(m.hashesperid, r.hashesperid)
+    assert int(np.sum(r.counts > 37)) == 4                                    # the merge did overflow
+    lines = lambda s: [ln for ln in s.splitlines() if ln.startswith("hash_table ")]     # noqa: E731
+    assert lines(out["mirror"][1]) == lines(out["ref"][1]) and len(lines(out["ref"][1])) == 2
