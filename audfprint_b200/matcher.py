@@ -9,8 +9,12 @@ the same machine), `max_returns` truncation and message formatting.
 The optional second-wave flags — exact_count, find_time_range and
 match_hashes(hashesfor=...) — take the hits (afp_get_hits) and the ranked candidate list
 (afp_match_batch, publish_candidates) from the device and finish on the host with the
-reference's per-candidate post-processing restated below (audfprint_match.py:149-244);
-that part is O(search_depth) small NumPy calls per query, as in the reference.
+reference's per-candidate post-processing (audfprint_match.py:149-244) restated twice:
+query by query (_match_with_options: O(search_depth) small NumPy calls per query, as in the
+reference; used for a single query and for hashesfor) and for a whole batch in array
+operations (_finish_options_batch: sparse offset histograms, supports by bisection, distinct
+pairs and time quantiles by sorting - no per-query Python work; match_batch uses it).
+tests/test_host_mirror_cpu.py holds the two equal row for row.
 illustrate (matplotlib) is not provided.
 """
 from __future__ import annotations
@@ -107,11 +111,17 @@ class Matcher(object):
                 r = self._match_with_options(ht, packed)
                 return [r[(-r[:, 1]).argsort(), ] if sort else r]
             hits = ht.get_hits(packed)
-            mask =(1 << int(ht.hashbits)) - 1
+            mask = (1 << int(ht.hashbits)) - 1
             per_row = np.minimum(int(ht.depth), ht.counts[packed[:, 1].astype(np.int64) & mask]).astype(np.int64)
             hoff = np.concatenate([[0], np.cumsum(per_row)])[qoff]
             rows, roff, cand, cnts = self._publish_call(ht, packed, qoff)
-            out = []
+            if self.threshcount >= 1:
+                # the whole batch in one vectorised pass (no per-query Python work)
+                out, ooff = self._finish_options_batch(hits, hoff, rows, roff, cand, cnts)
+                if sort and len(out):
+                    out = self._sort_by_count(out, ooff)
+                return [out[ooff[i]:ooff[i + 1]] for i in range(nq)]
+            out = []                             # threshcount < 1: empty offset bins can be modes
             for i in range(nq):
                 pre = (hits[hoff[i]:hoff[i + 1]], rows[roff[i]:roff[i + 1]], cand[i], cnts[i])
                 out.append(self._match_with_options(ht, packed[qoff[i]:qoff[i + 1]], device_results=pre))
@@ -219,6 +229,132 @@ class Matcher(object):
         timebits = max(1, int(np.ceil(np.log(max(1, int(hits[:, 3].max()))) / np.log(2))))
         keys = self._pair_keys(self._support(by_id, srt[hashesfor, 0], srt[hashesfor, 2]), timebits)
         return rows, np.c_[keys & ((1 << timebits) - 1), keys >> timebits]
+
+    def _finish_options_batch(self, hits, hoff, rows, roff, cand, cnts):
+        """exact_count / find_time_range post-processing (audfprint_match.py:149-244) of a WHOLE
+        batch in array operations - the same rows, in the same order, as _match_with_options
+        query by query (needs threshcount >= 1: with 0 the reference also reports empty offset
+        bins as modes, which only the dense per-query histogram represents).
+
+        hits  (H,4) [id, dtime, hash, qtime] of all queries, hoff (nq+1) their offsets
+        rows  (R,7) approximate rows of the publish-mode device call, roff (nq+1)
+        cand  (nq, search_depth, 3) [id, raw, weight] ranked candidates, cnts (nq,2) [entries, n_above]
+        Returns (rows (R',7) int32 in (query, candidate rank, offset) order, offsets (nq+1))."""
+        nq = len(hoff) - 1
+        win = int(self.window)
+        depth = np.maximum(0, np.minimum(np.minimum(cnts[:, 1].astype(np.int64), int(self.search_depth)),
+                                         cnts[:, 0].astype(np.int64)))
+        empty = (np.zeros((0, 7), np.int32), np.zeros(nq + 1, np.int64))
+        rq = np.repeat(np.arange(nq), np.diff(roff))
+        if not self.exact_count:
+            keep = rows[:, 4] < depth[rq]                      # publish mode also reports ids past maxdepth
+            out, oq = rows[keep].copy(), rq[keep]
+            ooff = np.concatenate([[0], np.cumsum(np.bincount(oq, minlength=nq))]).astype(np.int64)
+            if not self.find_time_range or len(out) == 0:
+                return out, ooff
+            # groups = the distinct (query, id) pairs of the kept rows
+            nid = int(max(out[:, 0].max(), hits[:, 0].max() if len(hits) else 0)) + 1
+            pair = oq.astype(np.int64) * nid + out[:, 0].astype(np.int64)
+            gkey, gidx = np.unique(pair, return_inverse=True)
+            srt = self._sorted_group_hits(hits, hoff, gkey, np.arange(len(gkey)), nid, win)
+            lo, hi = self._support_ranges(srt, gidx, out[:, 2].astype(np.int64), win)
+            tlo, thi = self._range_quantiles(srt, lo, hi)
+            out[:, 5], out[:, 6] = tlo, thi
+            return out, ooff
+        # ---- exact counts: groups = the ranked candidates, in (query, rank) order
+        cq = np.repeat(np.arange(nq), depth)
+        if len(cq) == 0 or len(hits) == 0:
+            return empty
+        crank = np.arange(len(cq)) - np.repeat(np.cumsum(depth) - depth, depth)
+        cid = cand[cq, crank, 0].astype(np.int64)
+        craw = cand[cq, crank, 1].astype(np.int64)
+        nid = int(max(cid.max(), hits[:, 0].max())) + 1
+        ckey = cq.astype(np.int64) * nid + cid
+        perm = np.argsort(ckey, kind="stable")
+        srt = self._sorted_group_hits(hits, hoff, ckey[perm], perm, nid, win)
+        sg, sdt = srt["g"], srt["dt"]
+        if len(sg) == 0:
+            return empty
+        # sparse offset histogram per group: runs of equal (group, offset)
+        first = np.r_[True, (sg[1:] != sg[:-1]) | (sdt[1:] != sdt[:-1])]
+        start = np.nonzero(first)[0]
+        ug, udt = sg[start], sdt[start]
+        ucnt = np.diff(np.r_[start, len(sg)])
+        adj_prev = np.r_[False, (ug[1:] == ug[:-1]) & (udt[1:] == udt[:-1] + 1)]
+        prev = np.where(adj_prev, np.r_[0, ucnt[:-1]], 0)
+        nxt = np.where(np.r_[adj_prev[1:], False], np.r_[ucnt[1:], 0], 0)
+        # local maximum of the dense histogram (locmax, audfprint_match.py:48-65) that reaches threshcount
+        is_mode = (ucnt >= prev) & (nxt < ucnt) & (ucnt >= int(self.threshcount))
+        mg, mode = ug[is_mode], udt[is_mode]
+        if len(mg) == 0:
+            return empty
+        lo, hi = self._support_ranges(srt, mg, mode, win)
+        # distinct (query time, hash) pairs inside every support (_unique_match_hashes, :149-171)
+        ln = hi - lo
+        mj = np.repeat(np.arange(len(mg)), ln)
+        src = np.repeat(lo, ln) + (np.arange(int(ln.sum())) - np.repeat(np.cumsum(ln) - ln, ln))
+        # packed exactly as the reference packs them: query time + (hash << bits of the query's
+        # largest time), encpowerof2 included - a largest time that is a power of two gets one bit
+        # too few there, and the (rare) collisions that follow are part of the reference's count
+        qmax = np.zeros(nq, np.int64)
+        nonempty = np.nonzero(np.diff(hoff))[0]
+        if len(nonempty):
+            qmax[nonempty] = np.maximum.reduceat(hits[:, 3].astype(np.int64), hoff[nonempty])
+        bits_of = {int(m): max(1, int(np.ceil(np.log(max(1, int(m))) / np.log(2)))) for m in np.unique(qmax)}
+        tbits = np.array([bits_of[int(m)] for m in qmax], np.int64)[cq[mg]]
+        pk = srt["qt"][src].astype(np.int64) + (srt["hash"][src].astype(np.int64) << tbits[mj])
+        o = np.lexsort((pk, mj))
+        mjs, pks = mj[o], pk[o]
+        new = np.r_[True, (mjs[1:] != mjs[:-1]) | (pks[1:] != pks[:-1])]
+        count = np.bincount(mjs[new], minlength=len(mg))
+        good = count >= int(self.threshcount)
+        out = np.zeros((int(good.sum()), 7), np.int32)
+        g = mg[good]
+        out[:, 0], out[:, 1], out[:, 2], out[:, 3], out[:, 4] = cid[g], count[good], mode[good], craw[g], crank[g]
+        if self.find_time_range and len(out):
+            out[:, 5], out[:, 6] = self._range_quantiles(srt, lo[good], hi[good])
+        ooff = np.concatenate([[0], np.cumsum(np.bincount(cq[g], minlength=nq))]).astype(np.int64)
+        return out, ooff
+
+    @staticmethod
+    def _sorted_group_hits(hits, hoff, sorted_keys, group_of_key, nid, win):
+        """Hits that belong to one of the (query, id) groups, ordered by (group, offset, query time).
+        sorted_keys: ascending query * nid + id of the groups; group_of_key: group number of each."""
+        hq = np.repeat(np.arange(len(hoff) - 1), np.diff(hoff))
+        hk = hq.astype(np.int64) * nid + hits[:, 0].astype(np.int64)
+        pos = np.minimum(np.searchsorted(sorted_keys, hk), len(sorted_keys) - 1)
+        sel = np.nonzero(sorted_keys[pos] == hk)[0]
+        g = np.asarray(group_of_key)[pos[sel]].astype(np.int64)
+        dt = hits[sel, 1].astype(np.int64)
+        qt = hits[sel, 3].astype(np.int64)
+        o = np.lexsort((qt, dt, g))
+        g, dt = g[o], dt[o]
+        dmin = int(dt.min()) if len(dt) else 0
+        span = (int(dt.max()) - dmin if len(dt) else 0) + 2 * win + 4
+        # one ascending key for bisection: group-major, offset-minor, with room for +-window probes
+        return {"g": g, "dt": dt, "qt": qt[o], "hash": hits[sel, 2][o], "dmin": dmin, "span": span,
+                "key": g * span + (dt - dmin + win + 1)}
+
+    @staticmethod
+    def _support_ranges(srt, group, mode, win):
+        """[lo, hi) into the sorted hits: the entries of `group` within `win` of offset `mode`."""
+        base = group.astype(np.int64) * srt["span"] + (mode - srt["dmin"] + win + 1)
+        return (np.searchsorted(srt["key"], base - win, side="left"),
+                np.searchsorted(srt["key"], base + win, side="right"))
+
+    def _range_quantiles(self, srt, lo, hi):
+        """Quantile-trimmed query-time support of every [lo, hi) range (_calculate_time_ranges,
+        audfprint_match.py:173-195): the times in ascending order, the reference's two indices."""
+        ln = hi - lo
+        j = np.repeat(np.arange(len(lo)), ln)
+        src = np.repeat(lo, ln) + (np.arange(int(ln.sum())) - np.repeat(np.cumsum(ln) - ln, ln))
+        t = srt["qt"][src]
+        t = t[np.lexsort((t, j))]
+        base = np.cumsum(ln) - ln
+        i_lo = (ln * float(self.time_quantile)).astype(np.int64)
+        i_hi = (ln * (1.0 - float(self.time_quantile))).astype(np.int64) - 1
+        i_hi = np.where(i_hi < 0, i_hi + ln, i_hi)               # Python's negative index
+        return t[base + i_lo], t[base + i_hi]
 
     def _publish_call(self, ht, qrows, qoff):
         """afp_match_batch with publish_candidates: (rows (R,7) with LOCAL ranks, row offsets,
