@@ -736,7 +736,8 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        per_step = min(max(cores * 4, 32), a.files)
+        # 16 files per worker per step: enough tasks that the pool's tail imbalance stays small
+        per_step = min(max(cores * 16, 128), a.files)
         tracks = make_tracks(pool, 0, per_step, a.seconds)
         pool.close()
         cpool = cpu_pool(tracks, cores)
