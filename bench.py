@@ -705,7 +705,8 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
                     help="BASELINE.json configs[]: 1 batch fingerprint (default; the driver's line), 2 match 10k "
                          "queries on 1 GPU, 3 ingest 180 s tracks incl. store, 4 sharded-table match of 100k queries")
-    ap.add_argument("--match-cpu-sample", type=int, default=128)
+    ap.add_argument("--match-cpu-sample", type=int, default=1024,
+                    help="queries in the CPU baseline / parity sample of the match leg (~3 s on 16 cores)")
     a = ap.parse_args()
     if a.match_queries is None:
         a.match_queries = 100000 if a.config == 4 else 10000
