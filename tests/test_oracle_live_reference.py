@@ -81,3 +81,81 @@ def test_oracle_equals_live_reference_on_fresh_seeds():
         want = np.array(ref["rows_%d" % seed], np.int32).reshape(-1, 7)
         assert rows.shape == want.shape and np.array_equal(rows[:1], want[:1]), seed   # best match identical
         assert sorted(map(tuple, rows[:, :4])) == sorted(map(tuple, want[:, :4]))        # same alignments
+
+
+_PARAM_DRIVER = r'''
+import json, random, sys
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(ref)r)
+import audfprint_analyze as an, audfprint_match as ma, audio_read as ar, hash_table as htm
+from audfprint_b200.synth import synth_track, synth_query, pcm_to_float
+pcm = {}
+ar.audio_read = lambda fn, sr=None, channels=None: (pcm_to_float(pcm[fn]), 11025)
+out = {}
+for k, (density, fanout, shifts, f_sd, maxpks) in enumerate(%(aparams)r):
+    for i in range(2):
+        pcm["t"] = synth_track(6000 + 10 * k + i, 9.0 + i)
+        a = an.Analyzer(density)
+        a.maxpairsperpeak, a.shifts, a.f_sd, a.maxpksperframe = fanout, shifts, f_sd, maxpks
+        out["h_%%d_%%d" %% (k, i)] = np.asarray(a.wavfile2hashes("t")).reshape(-1, 2).tolist()
+        if shifts == 1:
+            out["p_%%d_%%d" %% (k, i)] = np.asarray(a.wavfile2peaks("t")).reshape(-1, 2).tolist()
+# matcher parameters on a small overflowing table
+random.seed(9)
+ht = htm.HashTable(hashbits=12, depth=8, maxtime=1 << 14)
+trk = [synth_track(6500 + i, 12.0) for i in range(12)]
+for i, t in enumerate(trk):
+    pcm["t"] = t
+    ht.store("s%%d" %% i, an.Analyzer().wavfile2hashes("t"))
+out["table"] = ht.table.tolist(); out["counts"] = ht.counts.tolist(); out["hpi"] = np.asarray(ht.hashesperid).tolist()
+qs = []
+for j in range(4):
+    q, _ = synth_query(trk[3 * j], 900 + j, seconds=7.0, noise_sigma=0.01)
+    pcm["q"] = q
+    a = an.Analyzer(); a.shifts = 4
+    qs.append(np.asarray(a.wavfile2hashes("q"), np.int32).reshape(-1, 2))
+    out["q_%%d" %% j] = qs[-1].tolist()
+for k, (window, thresh, sdepth, maxal) in enumerate(%(mparams)r):
+    m = ma.Matcher()
+    m.window, m.threshcount, m.search_depth, m.max_alignments_per_id = window, thresh, sdepth, maxal
+    for j, qh in enumerate(qs):
+        out["rows_%%d_%%d" %% (k, j)] = np.asarray(m.match_hashes(ht, qh)).reshape(-1, 7).tolist()
+print("JSON" + json.dumps(out))
+'''
+
+ANALYZER_PARAMS = [(20.0, 3, 2, 30.0, 5), (20.0, 3, 3, 30.0, 5), (20.0, 3, 8, 30.0, 5), (35.0, 5, 1, 20.0, 3),
+                   (50.0, 6, 4, 30.0, 8), (10.0, 1, 1, 45.0, 1), (70.0, 8, 1, 30.0, 16)]
+MATCHER_PARAMS = [(0, 5, 100, 100), (3, 0, 5, 100), (1, 5, 1, 100), (2, 1, 100, 0), (2, 5, 0, 100), (1, 2, 3, 1)]
+
+
+def test_oracle_equals_live_reference_on_non_default_parameters():
+    """The parameter settings the GPU tests check against the ORACLE only
+    (test_non_default_analyzer_parameters_vs_oracle, test_matcher_edge_parameters_vs_oracle) -
+    density / fanout / shifts / f_sd / maxpksperframe and window / threshcount / search_depth /
+    max_alignments_per_id - checked here oracle vs LIVE reference, which closes the chain."""
+    code = _PARAM_DRIVER % {"root": ROOT, "ref": REF, "aparams": ANALYZER_PARAMS, "mparams": MATCHER_PARAMS}
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stderr[-2000:]
+    ref = json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("JSON")][0][4:])
+    for k, (density, fanout, shifts, f_sd, maxpks) in enumerate(ANALYZER_PARAMS):
+        for i in range(2):
+            d = pcm_to_float(synth_track(6000 + 10 * k + i, 9.0 + i))
+            got = orc.fingerprint(d, density=density, fanout=fanout, shifts=shifts, f_sd=f_sd, maxpks=maxpks)
+            assert np.array_equal(got, np.array(ref["h_%d_%d" % (k, i)], np.int32).reshape(-1, 2)), (k, i)
+            if shifts == 1:
+                pk = orc.find_peaks(d, density=density, f_sd=f_sd, maxpks=maxpks)
+                assert np.array_equal(np.array(pk, np.int32).reshape(-1, 2),
+                                      np.array(ref["p_%d_%d" % (k, i)], np.int32).reshape(-1, 2)), (k, i)
+    table, counts, hpi = np.array(ref["table"], np.uint32), np.array(ref["counts"], np.int32), np.array(ref["hpi"])
+    nexact = 0
+    for k, (window, thresh, sdepth, maxal) in enumerate(MATCHER_PARAMS):
+        for j in range(4):
+            qh = np.array(ref["q_%d" % j], np.int32).reshape(-1, 2)
+            want = np.array(ref["rows_%d_%d" % (k, j)], np.int32).reshape(-1, 7)
+            rows = orc.match_hashes(table, counts, 12, 8, 14, hpi, qh, window=window, threshcount=thresh,
+                                    search_depth=sdepth, max_alignments_per_id=maxal)
+            assert rows.shape == want.shape and np.array_equal(rows[:, 1], want[:, 1]), (k, j)
+            # rank order among equal weights / equal counts is implementation-defined in the reference
+            assert sorted(map(tuple, rows[:, :4])) == sorted(map(tuple, want[:, :4])), (k, j)
+            nexact += int(np.array_equal(rows, want))
+    assert nexact >= 12
