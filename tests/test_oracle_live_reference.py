@@ -159,3 +159,26 @@ def test_oracle_equals_live_reference_on_non_default_parameters():
             assert sorted(map(tuple, rows[:, :4])) == sorted(map(tuple, want[:, :4])), (k, j)
             nexact += int(np.array_equal(rows, want))
     assert nexact >= 12
+
+
+def test_spread_local_maxes_equals_reference_spreadpeaksinvector():
+    """The stand-alone method north_star names (audfprint_analyze.py:153-160): the oracle function
+    the GPU test compares afp_spread_peaks with, against the live reference's own method."""
+    code = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import audfprint_analyze as an
+rng = np.random.default_rng(12)
+out = []
+for n, width in [(256, 4.0), (256, 30.0), (64, 2.5), (17, 1.0), (300, 12.0), (1, 4.0)]:
+    v = rng.standard_normal(n) * 3
+    v[rng.integers(0, n, max(1, n // 9))] = 2.0          # plateaus / equal neighbours
+    out.append([n, width, v.tolist(), an.Analyzer().spreadpeaksinvector(v, width).tolist()])
+print("JSON" + json.dumps(out))
+''' % REF
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr[-2000:]
+    for n, width, v, want in json.loads([ln for ln in run.stdout.splitlines() if ln.startswith("JSON")][0][4:]):
+        got = orc.spread_local_maxes(np.array(v), orc.gaussian_table(n, width))
+        assert np.array_equal(got, np.array(want)), (n, width)
