@@ -32,7 +32,6 @@ AVMEDIA_TYPE_AUDIO = 1
 AV_SAMPLE_FMT_S16 = 1
 AVERROR_EOF = -541478725           # FFERRTAG('E','O','F',' ')
 AVERROR_EAGAIN = -11
-AV_OPT_SEARCH_CHILDREN = 1
 
 
 class AVRational(C.Structure):
@@ -84,7 +83,6 @@ def _load():
     u.av_get_sample_fmt_name.argtypes = [i]
     u.av_opt_get_chlayout.argtypes = [vp, C.c_char_p, i, p(AVChannelLayout)]
     u.av_channel_layout_default.argtypes = [p(AVChannelLayout), i]
-    u.av_get_bytes_per_sample.argtypes = [i]
     u.av_sample_fmt_is_planar.argtypes = [i]
     s.swr_alloc_set_opts2.argtypes = [p(vp), p(AVChannelLayout), i, i, p(AVChannelLayout), i, i, i, vp]
     s.swr_init.argtypes = [vp]
